@@ -1,0 +1,36 @@
+"""CPU oracle for the watsor detection hot path -- TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``oracle/`` is product code.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and only as the checker or the reported CPU
+baseline.  ``watsor_b200`` never imports it; the product path fails loudly when
+the CUDA library is missing.
+
+What it restates (all citations into /root/reference, asmirnou/watsor @127f125):
+
+* watsor/detection/tensorflow_cpu.py:74-121 -- feed a uint8 HWC frame to the
+  frozen TF Object-Detection graph, fetch detection_boxes/scores/classes, convert
+  the normalised boxes to integer pixel coordinates.
+* the arithmetic of the frozen graph itself (watsor/test/model/cpu.pb, produced by
+  watsor/test/model/prepare.py:19-198).  TensorFlow -- an un-pinned, un-vendored
+  dependency (setup.py:51-53, docker/Dockerfile.base:39) -- is NOT installed here,
+  so the graph is restated op-group by op-group from the GraphDef with numpy /
+  torch-CPU fp32 (see oracle/ssd_graph.py).  Every constant is read from the
+  GraphDef, none is hard-coded.
+* watsor/filter/{confidence,area,mask,track}.py and watsor/filter/sieve.py.
+  shapely (mask.py:2) is absent, so bbox/polygon intersection is restated as an
+  exact integer-geometry test (oracle/filters.py).
+
+PARITY PINNING STATUS
+  - filter stage: pinned by the reference's own known-answer tests
+    (watsor/test/test_filter.py:14-96), re-run against this oracle in
+    tests/test_oracle_filters.py.
+  - struct ABI: pinned by ctypes sizes/offsets of watsor/stream/share.py:11-32.
+  - conv / decode / NMS numerics: **parity unpinned**.  The reference holds no
+    golden boxes/scores for the TF graph (watsor/test/test_detect.py:28-77 only
+    asserts ">= 100 labelled detections with confidence >= 0.5"), and TensorFlow
+    cannot be run here.  The oracle is therefore checked against that same
+    behavioural assertion (Artist frames -> the drawn shapes are found with the
+    right class) and otherwise stands on its line-by-line restatement of the
+    GraphDef.
+"""

@@ -1,0 +1,10 @@
+#!/bin/bash
+# One gpurun call: parity tests, smoke, a short bench, the ncu launch list.  Logs -> gpurun_out/
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+echo "== pytest -m gpu" 
+timeout 900 python -m pytest tests -m gpu -q -x --timeout=600 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee gpurun_out/smoke.log
+echo "== bench"
+timeout 600 python bench.py --steps 30 --warmup 5 2>&1 | tail -3 | tee gpurun_out/bench.log

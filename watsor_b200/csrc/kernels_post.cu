@@ -1,0 +1,406 @@
+// kernels_post.cu -- K7 (anchor decode + sigmoid), K8 (per-class NMS, global top-100),
+// K9 (integer conversion + confidence / area / mask-zone predicates -> Detection[100]).
+//
+// Restates `Postprocessor/Decode/*`, `Postprocessor/convert_scores`, `Postprocessor/Slice`,
+// `Postprocessor/BatchMultiClassNonMaxSuppression/*` and the final `add` of the frozen graph
+// (watsor/detection/tensorflow_cpu.py:114), the python write loop tensorflow_cpu.py:79-90, and
+// watsor/filter/{confidence,area,mask}.py as applied by watsor/filter/track.py:26.
+//
+// Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in the graph's op
+// order, so that given identical head outputs the result is bit-identical to the oracle
+// (up to the last-ulp difference between CUDA's expf and the host libm's).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------- K7
+__device__ __forceinline__ float4 decode_box(float4 e, float4 a, const PostParams& pp) {
+  // anchors are corner boxes [ymin,xmin,ymax,xmax]  (get_center_coordinates_and_sizes)
+  float wa = __fsub_rn(a.w, a.y), ha = __fsub_rn(a.z, a.x);
+  float ycenter_a = __fadd_rn(a.x, __fdiv_rn(ha, 2.0f));
+  float xcenter_a = __fadd_rn(a.y, __fdiv_rn(wa, 2.0f));
+  float ty = __fdiv_rn(e.x, pp.scale_y), tx = __fdiv_rn(e.y, pp.scale_x);
+  float th = __fdiv_rn(e.z, pp.scale_h), tw = __fdiv_rn(e.w, pp.scale_w);
+  float w = __fmul_rn(expf(tw), wa), h = __fmul_rn(expf(th), ha);
+  float ycenter = __fadd_rn(__fmul_rn(ty, ha), ycenter_a);
+  float xcenter = __fadd_rn(__fmul_rn(tx, wa), xcenter_a);
+  float hh = __fdiv_rn(h, 2.0f), hw = __fdiv_rn(w, 2.0f);
+  return make_float4(__fsub_rn(ycenter, hh), __fsub_rn(xcenter, hw), __fadd_rn(ycenter, hh),
+                     __fadd_rn(xcenter, hw));
+}
+
+__device__ __forceinline__ float sigmoid_score(float logit, float logit_scale) {
+  float z = __fdiv_rn(logit, logit_scale);
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z)));
+}
+
+constexpr int DEC_TILE = 128;
+
+// grid (ceil(N/DEC_TILE), frames).  Decodes DEC_TILE boxes, then sweeps the [DEC_TILE][C+1] logit tile
+// with coalesced loads; every (anchor, class) with score > threshold is appended to the candidate
+// list of (frame, class) as key = score_bits << 32 | ~anchor  (sorting keys descending gives
+// "score descending, lower anchor index first", the pop order of TF's NonMaxSuppressionV5).
+__global__ void __launch_bounds__(256)
+    k_decode_scores(PostParams pp, const float* __restrict__ enc, const float* __restrict__ logits,
+                    const float* __restrict__ anchors, float4* __restrict__ dec, int* __restrict__ cand_count,
+                    unsigned long long* __restrict__ cand) {
+  const int f = blockIdx.y, a0 = blockIdx.x * DEC_TILE;
+  const int N = pp.num_anchors, C = pp.num_classes, C1 = C + 1;
+  const int na = min(DEC_TILE, N - a0);
+  if ((int)threadIdx.x < na) {
+    int i = a0 + threadIdx.x;
+    float4 e = reinterpret_cast<const float4*>(enc)[(size_t)f * N + i];
+    float4 a = reinterpret_cast<const float4*>(anchors)[i];
+    dec[(size_t)f * N + i] = decode_box(e, a, pp);
+  }
+  const float* lt = logits + ((size_t)f * N + a0) * C1;
+  const int total = na * C1;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int il = e / C1, c = e - il * C1;
+    if (c == 0) continue;  // `Postprocessor/Slice`: background column dropped after the sigmoid
+    float s = sigmoid_score(lt[e], pp.logit_scale);
+    if (s > pp.score_thr) {
+      int pos = atomicAdd(&cand_count[f * C + (c - 1)], 1);
+      cand[((size_t)f * C + (c - 1)) * N + pos] =
+          ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(a0 + il));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- K8
+// TF non_max_suppression_op.cc IOU<float>() -- same op order, separately rounded
+__device__ __forceinline__ float iou_tf(float4 bi, float4 bj) {
+  float ymin_i = fminf(bi.x, bi.z), xmin_i = fminf(bi.y, bi.w);
+  float ymax_i = fmaxf(bi.x, bi.z), xmax_i = fmaxf(bi.y, bi.w);
+  float ymin_j = fminf(bj.x, bj.z), xmin_j = fminf(bj.y, bj.w);
+  float ymax_j = fmaxf(bj.x, bj.z), xmax_j = fmaxf(bj.y, bj.w);
+  float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
+  float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
+  if (area_i <= 0.f || area_j <= 0.f) return 0.f;
+  float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
+  float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
+  float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+}
+
+__device__ __forceinline__ float4 clip_unit(float4 b) {  // ClipToWindow [0,0,1,1]
+  return make_float4(fmaxf(fminf(b.x, 1.f), 0.f), fmaxf(fminf(b.y, 1.f), 0.f), fmaxf(fminf(b.z, 1.f), 0.f),
+                     fmaxf(fminf(b.w, 1.f), 0.f));
+}
+
+// grid (classes, frames), 256 threads.  Bitonic sort of the candidate keys in shared memory, then
+// warp 0 runs the greedy suppression: 32 candidates are fetched per round, each is tested against
+// the kept boxes (<= 128, in shared memory) by all lanes at once and a ballot decides.
+// Output: merge keys  score_bits << 32 | (0xFFFF - class) << 16 | (0xFFFF - rank)  for the kept
+// boxes whose window-clipped area is positive (0 otherwise), plus the anchor index of every kept box.
+__global__ void __launch_bounds__(256)
+    k_nms(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ cand_count,
+          const unsigned long long* __restrict__ cand, int sort_cap, int* __restrict__ sel_count,
+          unsigned long long* __restrict__ sel_key, int* __restrict__ sel_idx) {
+  extern __shared__ unsigned long long s_keys[];  // [sort_cap]
+  __shared__ float4 s_kept[128];
+  const int c = blockIdx.x, f = blockIdx.y, C = pp.num_classes, N = pp.num_anchors;
+  const int n = min(cand_count[f * C + c], N);
+  const int max_out = min(pp.max_per_class, N);
+  unsigned long long* out_key = sel_key + ((size_t)f * C + c) * pp.max_per_class;
+  int* out_idx = sel_idx + ((size_t)f * C + c) * pp.max_per_class;
+  for (int i = threadIdx.x; i < pp.max_per_class; i += blockDim.x) out_key[i] = 0ull;
+  if (n == 0) {
+    if (threadIdx.x == 0) sel_count[f * C + c] = 0;
+    return;
+  }
+  int P = 32;
+  while (P < n) P <<= 1;
+  const unsigned long long* ck = cand + ((size_t)f * C + c) * N;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? ck[i] : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = s_keys[i], b = s_keys[ixj];
+          bool desc = (i & k) == 0;  // descending overall
+          if (desc ? a < b : a > b) {
+            s_keys[i] = b;
+            s_keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const float4* fdec = dec + (size_t)f * N;
+  int nkept = 0;
+  for (int base = 0; base < n && nkept < max_out; base += 32) {
+    int my = base + lane;
+    unsigned long long key = my < n ? s_keys[my] : 0ull;
+    unsigned idx = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+    float4 box = my < n ? fdec[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = min(32, n - base);
+    for (int t = 0; t < cnt && nkept < max_out; ++t) {
+      float4 bi;
+      bi.x = __shfl_sync(0xffffffffu, box.x, t);
+      bi.y = __shfl_sync(0xffffffffu, box.y, t);
+      bi.z = __shfl_sync(0xffffffffu, box.z, t);
+      bi.w = __shfl_sync(0xffffffffu, box.w, t);
+      bool sup = false;
+      for (int j = lane; j < nkept; j += 32) sup |= iou_tf(bi, s_kept[j]) > pp.iou_thr;
+      if (!__any_sync(0xffffffffu, sup)) {
+        if (lane == t) {
+          s_kept[nkept] = box;
+          float4 cb = clip_unit(box);
+          float area = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
+          out_idx[nkept] = (int)idx;
+          out_key[nkept] = area > 0.f ? ((key & 0xFFFFFFFF00000000ull) |
+                                         ((unsigned long long)(0xFFFFu - (unsigned)c) << 16) |
+                                         (unsigned long long)(0xFFFFu - (unsigned)nkept))
+                                      : 0ull;
+        }
+        ++nkept;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) sel_count[f * C + c] = nkept;
+}
+
+// ------------------------------------------------------------------------------------------- K9
+__device__ __forceinline__ int sat_count(const int32_t* s, int W1, int x0, int y0, int x1, int y1) {
+  return s[(size_t)(y1 + 1) * W1 + (x1 + 1)] - s[(size_t)y0 * W1 + (x1 + 1)] - s[(size_t)(y1 + 1) * W1 + x0] +
+         s[(size_t)y0 * W1 + x0];
+}
+
+// The lazily evaluated predicate chain of watsor/filter/track.py:26.
+__device__ uint32_t apply_filters(const CameraCfg* __restrict__ cam, wb_detection* d, bool write_zones) {
+  uint32_t v = 0;
+  const int lab = d->label;
+  if (cam == nullptr) return lab > 0 ? WB_V_LABEL : 0u;
+  if (cam->check_label) {
+    if (!(lab > 0)) return v;
+    v |= WB_V_LABEL;
+  }
+  bool present = lab >= 0 && lab < WB_MAX_LABELS && cam->present[lab];
+  double conf_thr, area_thr;
+  uint32_t allowed;
+  if (present) {
+    conf_thr = cam->conf[lab];
+    area_thr = cam->area[lab];
+    allowed = cam->has_zone_list[lab] ? cam->zone_bits[lab] : 0xFFFFFFFFu;
+  } else if (cam->default_present) {
+    present = true;
+    conf_thr = cam->default_conf;
+    area_thr = cam->default_area;
+    allowed = cam->default_has_zone_list ? cam->default_zone_bits : 0xFFFFFFFFu;
+  } else {
+    return v;  // confidence.py:18 / area.py:21: `... is not None and ...`
+  }
+  // confidence.py:17-19
+  if (!(d->confidence >= conf_thr)) return v;
+  v |= WB_V_CONFIDENCE;
+  // area.py:20-26  abs((x_max - x_min + 1) * (y_max - y_min + 1)) >= pct/100 * W*H
+  const wb_bounding_box bb = d->bounding_box;
+  long long a = (long long)(bb.x_max - bb.x_min + 1) * (long long)(bb.y_max - bb.y_min + 1);
+  if (a < 0) a = -a;
+  if (!((double)a >= area_thr)) return v;
+  v |= WB_V_AREA;
+  if (cam->has_mask) {
+    // mask.py:44-59: closed bbox rectangle intersects zone polygon  <=>  it covers >= 1 pixel of the
+    // filled-contour raster (summed-area table, 4 loads per zone)
+    int xa = min(bb.x_min, bb.x_max), xb = max(bb.x_min, bb.x_max);
+    int ya = min(bb.y_min, bb.y_max), yb = max(bb.y_min, bb.y_max);
+    xa = max(xa, 0);
+    ya = max(ya, 0);
+    xb = min(xb, cam->width - 1);
+    yb = min(yb, cam->height - 1);
+    bool hit = false;
+    int z = 0;
+    if (xa <= xb && ya <= yb) {
+      const int W1 = cam->width + 1;
+      const size_t plane = (size_t)(cam->height + 1) * W1;
+      for (int p = 0; p < cam->n_zones && z < WB_MAX_ZONES; ++p) {
+        if (!((allowed >> p) & 1u)) continue;
+        if (sat_count(cam->sat + p * plane, W1, xa, ya, xb, yb) > 0) {
+          if (write_zones) d->zones[z] = p + 1;
+          ++z;
+          hit = true;
+        }
+      }
+    }
+    if (!hit) return v;
+    v |= WB_V_MASK;
+  }
+  return v | WB_V_PASS;
+}
+
+// One block per frame.  (1) merge keys of all classes -> shared memory; (2) warp 0 does the C-way
+// merge of the per-class sorted lists = `SortByField` (TopKV2, ties -> lower concat index) restricted
+// to boxes with positive clipped area, top max_total; (3) one thread per output row: clip, `add` +1,
+// tensorflow_cpu.py:79-90 integer conversion, predicates, Detection write.
+__global__ void __launch_bounds__(128)
+    k_merge_filter(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ sel_count,
+                   const unsigned long long* __restrict__ sel_key, const int* __restrict__ sel_idx,
+                   const FrameDesc* __restrict__ frames, const CameraCfg* __restrict__ cams, uint32_t flags,
+                   wb_detection* __restrict__ out, uint32_t* __restrict__ verdicts, float* __restrict__ raw_boxes,
+                   float* __restrict__ raw_scores, float* __restrict__ raw_classes, int* __restrict__ raw_num) {
+  extern __shared__ unsigned long long s_all[];  // [C][max_per_class]
+  __shared__ unsigned long long s_win[128];
+  __shared__ int s_nvalid;
+  const int f = blockIdx.x, C = pp.num_classes, MP = pp.max_per_class, N = pp.num_anchors;
+  const unsigned long long* keys = sel_key + (size_t)f * C * MP;
+  for (int i = threadIdx.x; i < C * MP; i += blockDim.x) s_all[i] = keys[i];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int ptr[4], cnt[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int c = lane + 32 * t;
+      cnt[t] = c < C ? sel_count[f * C + c] : 0;
+      ptr[t] = 0;
+      while (ptr[t] < cnt[t] && s_all[c * MP + ptr[t]] == 0ull) ++ptr[t];
+    }
+    int r = 0;
+    for (; r < pp.max_total; ++r) {
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        int c = lane + 32 * t;
+        if (ptr[t] < cnt[t]) best = max(best, s_all[c * MP + ptr[t]]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (best == 0ull) break;
+      int c = 0xFFFF - (int)((best >> 16) & 0xFFFFull);
+      if ((c & 31) == lane) {
+        int t = c >> 5;
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+          if (tt == t) {
+            ++ptr[tt];
+            while (ptr[tt] < cnt[tt] && s_all[c * MP + ptr[tt]] == 0ull) ++ptr[tt];
+          }
+        s_win[r] = best;
+      }
+    }
+    if (lane == 0) s_nvalid = r;
+  }
+  __syncthreads();
+  const int nvalid = s_nvalid;
+  const int r = threadIdx.x;
+  if (r == 0 && raw_num) raw_num[f] = nvalid;
+  if (r >= WB_MAX_DETECTIONS) return;
+  float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+  float score = 0.f, cls = 0.f;
+  if (r < nvalid && r < pp.max_total) {
+    unsigned long long k = s_win[r];
+    int c = 0xFFFF - (int)((k >> 16) & 0xFFFFull), rank = 0xFFFF - (int)(k & 0xFFFFull);
+    score = __uint_as_float((unsigned)(k >> 32));
+    cls = (float)c;
+    int idx = sel_idx[((size_t)f * C + c) * MP + rank];
+    box = clip_unit(dec[(size_t)f * N + idx]);
+  }
+  cls = __fadd_rn(cls, pp.class_offset);  // graph node `add` (+1 also on the zero padding)
+  if (raw_boxes) {
+    reinterpret_cast<float4*>(raw_boxes)[(size_t)f * WB_MAX_DETECTIONS + r] = box;
+    raw_scores[(size_t)f * WB_MAX_DETECTIONS + r] = score;
+    raw_classes[(size_t)f * WB_MAX_DETECTIONS + r] = cls;
+  }
+  const FrameDesc fd = frames[f];
+  wb_detection d;
+  d.label = (int)cls;
+  for (int z = 0; z < WB_MAX_ZONES; ++z) d.zones[z] = 0;
+  d.confidence = (double)score;
+  // int(np.float32 * int): exact product (float64), truncation toward zero
+  const double mh = (double)(fd.h - 1), mw = (double)(fd.w - 1);
+  d.bounding_box.y_min = (int)((double)box.x * mh);
+  d.bounding_box.x_min = (int)((double)box.y * mw);
+  d.bounding_box.y_max = (int)((double)box.z * mh);
+  d.bounding_box.x_max = (int)((double)box.w * mw);
+  const CameraCfg* cam = (cams != nullptr && fd.cam >= 0) ? cams + fd.cam : nullptr;
+  uint32_t v = apply_filters(cam, &d, (flags & WB_F_FUSE_FILTERS) != 0);
+  out[(size_t)f * WB_MAX_DETECTIONS + r] = d;
+  if (verdicts) verdicts[(size_t)f * WB_MAX_DETECTIONS + r] = v;
+}
+
+void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* enc, const float* logits,
+                 const float* anchors, const FrameDesc* frames, const CameraCfg* cams, uint32_t flags,
+                 float* dec_boxes, int* cand_count, unsigned long long* cand, int* sel_count,
+                 unsigned long long* sel, wb_detection* out, uint32_t* verdicts, float* raw_boxes,
+                 float* raw_scores, float* raw_classes, int* raw_num) {
+  const int C = pp.num_classes, N = pp.num_anchors;
+  cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)n * C, lc.stream);
+  dim3 g1((N + DEC_TILE - 1) / DEC_TILE, n);
+  k_decode_scores<<<g1, 256, 0, lc.stream>>>(pp, enc, logits, anchors, reinterpret_cast<float4*>(dec_boxes),
+                                             cand_count, cand);
+  ++*lc.launch_counter;
+  int sort_cap = 32;
+  while (sort_cap < N) sort_cap <<= 1;
+  // sel holds keys [n][C][max_per_class] followed by anchor indices (int) of the same shape
+  unsigned long long* sel_key = sel;
+  int* sel_idx = reinterpret_cast<int*>(sel + (size_t)n * C * pp.max_per_class);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  k_nms<<<dim3(C, n), 256, sizeof(unsigned long long) * sort_cap, lc.stream>>>(
+      pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx);
+  ++*lc.launch_counter;
+  k_merge_filter<<<n, 128, sizeof(unsigned long long) * (size_t)C * pp.max_per_class, lc.stream>>>(
+      pp, reinterpret_cast<const float4*>(dec_boxes), sel_count, sel_key, sel_idx, frames, cams, flags, out,
+      verdicts, raw_boxes, raw_scores, raw_classes, raw_num);
+  ++*lc.launch_counter;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone predicate chain on caller rows (ConfidenceFilter / AreaFilter / MaskFilter __call__)
+__global__ void k_filter_rows(const CameraCfg* __restrict__ cam, int n_rows, wb_detection* __restrict__ rows,
+                              uint32_t* __restrict__ verdicts) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  wb_detection d = rows[r];
+  uint32_t v = apply_filters(cam, &d, true);
+  rows[r] = d;
+  verdicts[r] = v;
+}
+void launch_filter_rows(const LaunchCtx& lc, const CameraCfg* cam, int n_rows, wb_detection* rows,
+                        uint32_t* verdicts) {
+  k_filter_rows<<<(n_rows + 127) / 128, 128, 0, lc.stream>>>(cam, n_rows, rows, verdicts);
+  ++*lc.launch_counter;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// summed-area tables of the zone rasters (MaskFilter.__init__): sat[z][y][x] = #zone pixels in
+// rows < y, cols < x.  Two passes (row scan, column scan); set-up time only.
+__global__ void k_sat_rows(const uint8_t* __restrict__ raster, int n_zones, int h, int w, int32_t* __restrict__ sat) {
+  int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (y > h) return;
+  int32_t* row = sat + ((size_t)z * (h + 1) + y) * (w + 1);
+  row[0] = 0;
+  if (y == 0) {
+    for (int x = 1; x <= w; ++x) row[x] = 0;
+    return;
+  }
+  const uint8_t* src = raster + ((size_t)z * h + (y - 1)) * w;
+  int run = 0;
+  for (int x = 0; x < w; ++x) {
+    run += src[x] ? 1 : 0;
+    row[x + 1] = run;
+  }
+}
+__global__ void k_sat_cols(int n_zones, int h, int w, int32_t* __restrict__ sat) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (x > w) return;
+  int32_t* base = sat + (size_t)z * (h + 1) * (w + 1) + x;
+  int run = 0;
+  for (int y = 0; y <= h; ++y) {
+    run += base[(size_t)y * (w + 1)];
+    base[(size_t)y * (w + 1)] = run;
+  }
+}
+void launch_build_sat(const LaunchCtx& lc, const uint8_t* raster, int n_zones, int h, int w, int32_t* sat) {
+  k_sat_rows<<<dim3((h + 1 + 127) / 128, n_zones), 128, 0, lc.stream>>>(raster, n_zones, h, w, sat);
+  k_sat_cols<<<dim3((w + 1 + 127) / 128, n_zones), 128, 0, lc.stream>>>(n_zones, h, w, sat);
+  *lc.launch_counter += 2;
+}

@@ -1,0 +1,190 @@
+// kernels_pre.cu -- K1 (resize + normalise) and the fused K1+K2 stem convolution.
+//
+// Restates graph nodes `Cast`, `Preprocessor/map/while/ResizeImage/resize/ResizeBilinear`
+// (align_corners=false, half_pixel_centers=false), `Preprocessor/mul`, `Preprocessor/sub` and
+// `FeatureExtractor/.../Conv2d_0/{Conv2D,BatchNorm,Relu6}` of the frozen graph that
+// watsor/detection/tensorflow_cpu.py:114 runs.  Compiled with -fmad=false: the bilinear lerp is
+// a chain of separately rounded fp32 ops, exactly like TF's CPU kernel, so K1 is bit-exact
+// against the oracle.
+#include "common.cuh"
+
+struct AxisTap {
+  int lo, hi;
+  float lerp;
+};
+
+// TF legacy sampling: scale = in/(float)out; pos = dst*scale; lo = floor(pos);
+// hi = min(ceil(pos), in-1); lerp = pos - floor(pos).
+__device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, int out_size) {
+  float scale = __fdiv_rn((float)in_size, (float)out_size);
+  float pos = __fmul_rn((float)dst, scale);
+  float fl = floorf(pos);
+  AxisTap t;
+  t.lo = max((int)fl, 0);
+  t.hi = min((int)ceilf(pos), in_size - 1);
+  t.lerp = __fsub_rn(pos, fl);
+  return t;
+}
+
+__device__ __forceinline__ float lerp_px(float tl, float tr, float bl, float br, float lx, float ly) {
+  float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+  float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+  return __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+}
+
+// one resized + normalised pixel (3 channels)
+__device__ __forceinline__ void resized_pixel(const uint8_t* __restrict__ img, int w, const AxisTap& ty,
+                                              const AxisTap& tx, float mul, float sub, float* out3) {
+  const uint8_t* r0 = img + (size_t)ty.lo * w * 3;
+  const uint8_t* r1 = img + (size_t)ty.hi * w * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float tl = (float)__ldg(r0 + tx.lo * 3 + c), tr = (float)__ldg(r0 + tx.hi * 3 + c);
+    float bl = (float)__ldg(r1 + tx.lo * 3 + c), br = (float)__ldg(r1 + tx.hi * 3 + c);
+    float v = lerp_px(tl, tr, bl, br, tx.lerp, ty.lerp);
+    out3[c] = __fsub_rn(__fmul_rn(mul, v), sub);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 stand-alone: u8 HWC (any size) -> f32 [n][oh][ow][3].  Used by wb_preprocess (parity tests)
+// and by wb_backbone-less debugging; the production path is the fused stem below.
+__global__ void __launch_bounds__(256) k_preprocess_f32(const FrameDesc* __restrict__ frames,
+                                                        float* __restrict__ out, int oh, int ow, float mul,
+                                                        float sub) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= oh * ow) return;
+  FrameDesc fd = frames[blockIdx.y];
+  int oy = p / ow, ox = p - oy * ow;
+  AxisTap ty = axis_tap(oy, fd.h, oh), tx = axis_tap(ox, fd.w, ow);
+  float v[3];
+  resized_pixel(fd.ptr, fd.w, ty, tx, mul, sub, v);
+  float* o = out + ((size_t)blockIdx.y * oh * ow + p) * 3;
+  o[0] = v[0];
+  o[1] = v[1];
+  o[2] = v[2];
+}
+
+void launch_preprocess_f32(const LaunchCtx& lc, const FrameDesc* frames, int n, float* out, int oh, int ow,
+                           float mul, float sub) {
+  dim3 grid((oh * ow + 255) / 256, n);
+  k_preprocess_f32<<<grid, 256, 0, lc.stream>>>(frames, out, oh, ow, mul, sub);
+  ++*lc.launch_counter;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused stem: resized tile built in shared memory (the 300x300x3 tensor never reaches HBM), then the
+// first KxK stride-S convolution (C_in = 3) + folded BatchNorm + ReLU6.
+// Tile = 8 x 32 output pixels, one thread per output pixel, output channels in chunks of 16.
+constexpr int ST_TY = 8, ST_TX = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(ST_TY* ST_TX)
+    k_stem(const FrameDesc* __restrict__ frames, const float* __restrict__ pre, wb_layer L, int in_h, int in_w,
+           float mul, float sub, const float* __restrict__ w, const float* __restrict__ scale,
+           const float* __restrict__ offset, T* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int K = L.kh, S = L.stride;
+  const int tile_h = (ST_TY - 1) * S + K, tile_w = (ST_TX - 1) * S + K;
+  float* s_in = smem;                              // [tile_h][tile_w][3]
+  float* s_w = smem + tile_h * tile_w * 3;         // [K*K*3][n_pad]
+  const int f = blockIdx.z;
+  const int oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < K * K * 3 * (int)L.n_pad; i += blockDim.x) s_w[i] = w[i];
+
+  // resized tile; rows/cols outside the 300x300 image are the SAME-padding zeros
+  const int ry0 = oy0 * S - (int)L.pad_t, rx0 = ox0 * S - (int)L.pad_l;
+  FrameDesc fd;
+  if (pre == nullptr) fd = frames[f];
+  for (int i = tid; i < tile_h * tile_w; i += blockDim.x) {
+    int ly = i / tile_w, lx = i - ly * tile_w;
+    int ry = ry0 + ly, rx = rx0 + lx;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ry >= 0 && ry < in_h && rx >= 0 && rx < in_w) {
+      if (pre != nullptr) {
+        const float* p = pre + (((size_t)f * in_h + ry) * in_w + rx) * 3;
+        v[0] = p[0];
+        v[1] = p[1];
+        v[2] = p[2];
+      } else {
+        AxisTap ty = axis_tap(ry, fd.h, in_h), tx = axis_tap(rx, fd.w, in_w);
+        resized_pixel(fd.ptr, fd.w, ty, tx, mul, sub, v);
+      }
+    }
+    s_in[i * 3 + 0] = v[0];
+    s_in[i * 3 + 1] = v[1];
+    s_in[i * 3 + 2] = v[2];
+  }
+  __syncthreads();
+
+  const int ty = tid / ST_TX, tx = tid - ty * ST_TX;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy >= (int)L.out_h || ox >= (int)L.out_w) return;
+  T* o = out + (((size_t)f * L.out_h + oy) * L.out_w + ox) * L.out_c;
+  const int taps = K * K * 3;
+  for (int oc0 = 0; oc0 < (int)L.out_c; oc0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < K; ++ky)
+      for (int kx = 0; kx < K; ++kx) {
+        const float* ip = s_in + ((ty * S + ky) * tile_w + tx * S + kx) * 3;
+        const float* wp = s_w + (size_t)((ky * K + kx) * 3) * L.n_pad + oc0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float x = ip[c];
+          const float4* w4 = reinterpret_cast<const float4*>(wp + c * L.n_pad);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 ww = w4[q];
+            acc[q * 4 + 0] = fmaf(x, ww.x, acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(x, ww.y, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(x, ww.z, acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(x, ww.w, acc[q * 4 + 3]);
+          }
+        }
+      }
+    (void)taps;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int oc = oc0 + q * 4;
+      if (oc >= (int)L.out_c) break;
+      float4 v;
+      v.x = affine_rn(acc[q * 4 + 0], scale[oc + 0], offset[oc + 0]);
+      v.y = affine_rn(acc[q * 4 + 1], scale[oc + 1], offset[oc + 1]);
+      v.z = affine_rn(acc[q * 4 + 2], scale[oc + 2], offset[oc + 2]);
+      v.w = affine_rn(acc[q * 4 + 3], scale[oc + 3], offset[oc + 3]);
+      if (L.act == WB_ACT_RELU6) {
+        v.x = relu6f(v.x);
+        v.y = relu6f(v.y);
+        v.z = relu6f(v.z);
+        v.w = relu6f(v.w);
+      }
+      ActIO<T>::st4(o + oc, v);
+    }
+  }
+}
+
+template <typename T>
+void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre, int n, const wb_layer& L,
+                 int in_h, int in_w, float mul, float sub, const float* w, const float* scale,
+                 const float* offset, T* out) {
+  const int tile_h = (ST_TY - 1) * L.stride + L.kh, tile_w = (ST_TX - 1) * L.stride + L.kw;
+  size_t smem = ((size_t)tile_h * tile_w * 3 + (size_t)L.kh * L.kw * 3 * L.n_pad) * sizeof(float);
+  dim3 grid((L.out_w + ST_TX - 1) / ST_TX, (L.out_h + ST_TY - 1) / ST_TY, n);
+  static bool attr_done = false;
+  if (!attr_done && smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_stem<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  k_stem<T><<<grid, ST_TY * ST_TX, smem, lc.stream>>>(frames, pre, L, in_h, in_w, mul, sub, w, scale, offset, out);
+  ++*lc.launch_counter;
+}
+
+template void launch_stem<float>(const LaunchCtx&, const FrameDesc*, const float*, int, const wb_layer&, int,
+                                 int, float, float, const float*, const float*, const float*, float*);
+template void launch_stem<__nv_bfloat16>(const LaunchCtx&, const FrameDesc*, const float*, int,
+                                         const wb_layer&, int, int, float, float, const float*, const float*,
+                                         const float*, __nv_bfloat16*);

@@ -1,0 +1,724 @@
+// wb_api.cu -- the C-ABI of libwatsor_b200.so (include/watsor_b200.h): context, model upload,
+// per-camera filter state, the layer-program executor, two-slot asynchronous pipeline and the
+// stage-level entry points the parity tests use.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_tc.cuh"
+
+#define WB_MAX_CAMERAS 256
+#define WB_SLOTS 3
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(msg); \
+  } while (0)
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  FrameDesc* h_desc = nullptr;  // pinned
+  FrameDesc* d_desc = nullptr;
+  uint8_t* d_frames = nullptr;
+  size_t d_frames_cap = 0;
+  void* arena = nullptr;
+  float* d_pre = nullptr;
+  float *d_enc = nullptr, *d_logits = nullptr, *d_dec = nullptr;
+  int *d_cand_count = nullptr, *d_sel_count = nullptr;
+  unsigned long long *d_cand = nullptr, *d_sel = nullptr;
+  wb_detection *d_out = nullptr, *h_out = nullptr;
+  uint32_t *d_verdicts = nullptr, *h_verdicts = nullptr;
+  float *d_raw = nullptr, *h_raw = nullptr;  // boxes[n][100][4] scores[n][100] classes[n][100]
+  int *d_raw_num = nullptr, *h_raw_num = nullptr;
+  int n = 0;
+  uint32_t flags = 0;
+  bool busy = false;
+  int launches = 0;
+  // CUDA graph of the kernel sequence, keyed by (n, flags)
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_n = -1;
+  uint32_t graph_flags = 0;
+};
+
+struct wb_ctx {
+  int device = 0;
+  int max_batch = 0;
+  int precision = 0;
+  bool use_graph = true;
+  cudaDeviceProp prop;
+  wb_model_header hdr;
+  std::vector<wb_layer> layers;
+  std::vector<wb_tensor_entry> tensors;
+  float* d_weights = nullptr;
+  TcWeights tc;  // bf16 copies of the GEMM weights (precision 1)
+  PostParams pp;
+  CameraCfg* d_cams = nullptr;
+  std::vector<CameraCfg> h_cams;
+  std::vector<int32_t*> cam_sat;
+  Slot slots[WB_SLOTS];
+  cudaStream_t user_stream = nullptr;
+  bool has_user_stream = false;
+  int last_launches = 0;
+  std::vector<void*> registered;
+
+  const float* tensor(int idx) const { return d_weights + tensors[idx].offset; }
+  size_t elem_size() const { return precision == 1 ? 2 : 4; }
+  cudaStream_t stream_of(int s) { return has_user_stream ? user_stream : slots[s].stream; }
+};
+
+extern "C" {
+
+int wb_abi_version(void) { return WB_ABI_VERSION; }
+const char* wb_last_error(void) { return g_err.c_str(); }
+
+int wb_device_count(int* count) {
+  REQUIRE(count != nullptr, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return 0;
+}
+
+static int alloc_slot(wb_ctx* c, Slot& s) {
+  const int B = c->max_batch, N = c->hdr.num_anchors, C = c->hdr.num_classes, MP = c->hdr.max_per_class;
+  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&s.ev0));
+  CK(cudaEventCreate(&s.ev1));
+  CK(cudaMallocHost(&s.h_desc, sizeof(FrameDesc) * B));
+  CK(cudaMalloc(&s.d_desc, sizeof(FrameDesc) * B));
+  CK(cudaMalloc(&s.arena, (size_t)B * c->hdr.arena_elems * c->elem_size() + 1024));
+  CK(cudaMalloc(&s.d_pre, sizeof(float) * (size_t)B * c->hdr.input_h * c->hdr.input_w * 3));
+  CK(cudaMalloc(&s.d_enc, sizeof(float) * (size_t)B * N * 4));
+  CK(cudaMalloc(&s.d_logits, sizeof(float) * (size_t)B * N * (C + 1)));
+  CK(cudaMalloc(&s.d_dec, sizeof(float) * (size_t)B * N * 4));
+  CK(cudaMalloc(&s.d_cand_count, sizeof(int) * (size_t)B * C));
+  CK(cudaMalloc(&s.d_sel_count, sizeof(int) * (size_t)B * C));
+  CK(cudaMalloc(&s.d_cand, sizeof(unsigned long long) * (size_t)B * C * N));
+  CK(cudaMalloc(&s.d_sel, (sizeof(unsigned long long) + sizeof(int)) * (size_t)B * C * MP));
+  CK(cudaMalloc(&s.d_out, sizeof(wb_detection) * (size_t)B * WB_MAX_DETECTIONS));
+  CK(cudaMallocHost(&s.h_out, sizeof(wb_detection) * (size_t)B * WB_MAX_DETECTIONS));
+  CK(cudaMalloc(&s.d_verdicts, sizeof(uint32_t) * (size_t)B * WB_MAX_DETECTIONS));
+  CK(cudaMallocHost(&s.h_verdicts, sizeof(uint32_t) * (size_t)B * WB_MAX_DETECTIONS));
+  CK(cudaMalloc(&s.d_raw, sizeof(float) * (size_t)B * WB_MAX_DETECTIONS * 6));
+  CK(cudaMallocHost(&s.h_raw, sizeof(float) * (size_t)B * WB_MAX_DETECTIONS * 6));
+  CK(cudaMalloc(&s.d_raw_num, sizeof(int) * B));
+  CK(cudaMallocHost(&s.h_raw_num, sizeof(int) * B));
+  return 0;
+}
+
+int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_batch, int precision,
+              wb_ctx** out) {
+  REQUIRE(out != nullptr && model_blob != nullptr, "NULL argument");
+  REQUIRE(blob_bytes >= sizeof(wb_model_header), "model blob too small");
+  REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch out of range");
+  REQUIRE(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor core)");
+  CK(cudaSetDevice(device));
+  wb_ctx* c = new wb_ctx();
+  c->device = device;
+  c->max_batch = max_batch;
+  c->precision = precision;
+  if (const char* g = getenv("WB_NO_GRAPH")) c->use_graph = !(g[0] == '1');
+  CK(cudaGetDeviceProperties(&c->prop, device));
+  REQUIRE(c->prop.major == 10, std::string("libwatsor_b200 is built for sm_100a only; device is ") +
+                                   c->prop.name + " (sm_" + std::to_string(c->prop.major) +
+                                   std::to_string(c->prop.minor) + ")");
+  memcpy(&c->hdr, model_blob, sizeof(wb_model_header));
+  REQUIRE(memcmp(c->hdr.magic, WB_MODEL_MAGIC, 8) == 0, "bad model blob magic");
+  const uint8_t* p = static_cast<const uint8_t*>(model_blob) + sizeof(wb_model_header);
+  size_t need = sizeof(wb_model_header) + (size_t)c->hdr.n_layers * sizeof(wb_layer) +
+                (size_t)c->hdr.n_tensors * sizeof(wb_tensor_entry);
+  REQUIRE(blob_bytes >= need, "model blob truncated (tables)");
+  c->layers.resize(c->hdr.n_layers);
+  memcpy(c->layers.data(), p, c->layers.size() * sizeof(wb_layer));
+  p += c->layers.size() * sizeof(wb_layer);
+  c->tensors.resize(c->hdr.n_tensors);
+  memcpy(c->tensors.data(), p, c->tensors.size() * sizeof(wb_tensor_entry));
+  p += c->tensors.size() * sizeof(wb_tensor_entry);
+  size_t floats = 0;
+  for (auto& t : c->tensors) floats = std::max<size_t>(floats, t.offset + ((t.count + 63) / 64) * 64);
+  REQUIRE(blob_bytes >= need + floats * sizeof(float), "model blob truncated (data)");
+  REQUIRE(c->hdr.num_classes >= 1 && c->hdr.num_classes <= WB_MAX_LABELS, "num_classes must be in 1..128");
+  REQUIRE(c->hdr.max_per_class >= 1 && c->hdr.max_per_class <= 128, "max_per_class must be in 1..128");
+  REQUIRE(c->hdr.max_total >= 1 && c->hdr.max_total <= 128, "max_total must be in 1..128");
+  REQUIRE(c->hdr.score_thr >= 0.f, "negative score threshold is not supported");
+  REQUIRE(c->hdr.num_anchors >= 1 && c->hdr.num_anchors <= 16384, "num_anchors out of range");
+  for (auto& L : c->layers) {
+    if (L.op == WB_OP_PW || L.op == WB_OP_CONV || L.op == WB_OP_HEAD)
+      REQUIRE(L.in_c % 16 == 0, std::string("layer ") + L.name + ": in_c must be a multiple of 16");
+    if (L.op == WB_OP_DW) REQUIRE(L.out_c % 4 == 0 && L.kh == 3 && L.kw == 3, "depthwise must be 3x3, C%4==0");
+    if (L.op == WB_OP_PW || L.op == WB_OP_CONV) REQUIRE(L.out_c % 4 == 0, "out_c must be a multiple of 4");
+  }
+  CK(cudaMalloc(&c->d_weights, floats * sizeof(float)));
+  CK(cudaMemcpy(c->d_weights, p, floats * sizeof(float), cudaMemcpyHostToDevice));
+  if (precision == 1) {
+    std::string err;
+    if (tc_prepare_weights(c->layers, c->tensors, reinterpret_cast<const float*>(p), &c->tc, &err))
+      return fail("tensor-core weight preparation: " + err);
+  }
+  c->pp.num_anchors = c->hdr.num_anchors;
+  c->pp.num_classes = c->hdr.num_classes;
+  c->pp.scale_y = c->hdr.scale_y;
+  c->pp.scale_x = c->hdr.scale_x;
+  c->pp.scale_h = c->hdr.scale_h;
+  c->pp.scale_w = c->hdr.scale_w;
+  c->pp.logit_scale = c->hdr.logit_scale;
+  c->pp.iou_thr = c->hdr.iou_thr;
+  c->pp.score_thr = c->hdr.score_thr;
+  c->pp.max_per_class = c->hdr.max_per_class;
+  c->pp.max_total = c->hdr.max_total;
+  c->pp.class_offset = c->hdr.class_offset;
+  c->h_cams.assign(WB_MAX_CAMERAS, CameraCfg{});
+  c->cam_sat.assign(WB_MAX_CAMERAS, nullptr);
+  CK(cudaMalloc(&c->d_cams, sizeof(CameraCfg) * WB_MAX_CAMERAS));
+  CK(cudaMemset(c->d_cams, 0, sizeof(CameraCfg) * WB_MAX_CAMERAS));
+  for (int s = 0; s < WB_SLOTS; ++s)
+    if (alloc_slot(c, c->slots[s])) return 1;
+  CK(cudaDeviceSynchronize());
+  *out = c;
+  return 0;
+}
+
+int wb_destroy(wb_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* r : c->registered) cudaHostUnregister(r);
+  for (auto& s : c->slots) {
+    if (s.graph_exec) cudaGraphExecDestroy(s.graph_exec);
+    cudaFree(s.d_desc);
+    cudaFree(s.d_frames);
+    cudaFree(s.arena);
+    cudaFree(s.d_pre);
+    cudaFree(s.d_enc);
+    cudaFree(s.d_logits);
+    cudaFree(s.d_dec);
+    cudaFree(s.d_cand_count);
+    cudaFree(s.d_sel_count);
+    cudaFree(s.d_cand);
+    cudaFree(s.d_sel);
+    cudaFree(s.d_out);
+    cudaFree(s.d_verdicts);
+    cudaFree(s.d_raw);
+    cudaFree(s.d_raw_num);
+    cudaFreeHost(s.h_desc);
+    cudaFreeHost(s.h_out);
+    cudaFreeHost(s.h_verdicts);
+    cudaFreeHost(s.h_raw);
+    cudaFreeHost(s.h_raw_num);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  for (auto* p : c->cam_sat) cudaFree(p);
+  cudaFree(c->d_cams);
+  cudaFree(c->d_weights);
+  tc_free_weights(&c->tc);
+  delete c;
+  return 0;
+}
+
+int wb_device_name(wb_ctx* c, char* buf, size_t n) {
+  REQUIRE(c && buf && n > 0, "NULL argument");
+  snprintf(buf, n, "%s (cuda:%d, sm_%d%d, %s)", c->prop.name, c->device, c->prop.major, c->prop.minor,
+           c->precision == 1 ? "bf16 tcgen05" : "fp32");
+  return 0;
+}
+
+int wb_set_stream(wb_ctx* c, uint64_t stream) {
+  REQUIRE(c, "NULL ctx");
+  c->user_stream = reinterpret_cast<cudaStream_t>(stream);
+  c->has_user_stream = stream != 0;
+  for (auto& s : c->slots) s.graph_n = -1;  // graphs are stream-agnostic, but keep it simple
+  return 0;
+}
+
+int wb_model_info(wb_ctx* c, int32_t* ih, int32_t* iw, int32_t* nc, int32_t* na, int32_t* nl) {
+  REQUIRE(c, "NULL ctx");
+  if (ih) *ih = c->hdr.input_h;
+  if (iw) *iw = c->hdr.input_w;
+  if (nc) *nc = c->hdr.num_classes;
+  if (na) *na = c->hdr.num_anchors;
+  if (nl) *nl = c->hdr.n_layers;
+  return 0;
+}
+
+int wb_anchors(wb_ctx* c, float* out) {
+  REQUIRE(c && out, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(out, c->tensor(c->hdr.anchors_tensor), sizeof(float) * 4 * c->hdr.num_anchors,
+                cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int wb_set_camera(wb_ctx* c, int cam, int width, int height, int n_zones, const uint8_t* raster, int n_filters,
+                  const wb_class_filter* filters, uint32_t cam_flags) {
+  REQUIRE(c, "NULL ctx");
+  REQUIRE(cam >= 0 && cam < WB_MAX_CAMERAS, "cam_id out of range (0..255)");
+  REQUIRE(width > 0 && height > 0, "bad frame size");
+  REQUIRE(n_zones >= 0 && n_zones <= WB_MAX_CAMERA_ZONES, "a mask may hold at most 32 zones");
+  REQUIRE(n_zones == 0 || raster != nullptr, "zone_raster is NULL");
+  REQUIRE(n_filters == 0 || filters != nullptr, "filters is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());  // no batch may be reading the table while it changes
+  CameraCfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.width = width;
+  cfg.height = height;
+  cfg.n_zones = n_zones;
+  cfg.has_mask = raster != nullptr ? 1 : 0;
+  cfg.check_label = (cam_flags & WB_CAM_NO_LABEL_CHECK) ? 0 : 1;
+  for (int i = 0; i < n_filters; ++i) {
+    const wb_class_filter& f = filters[i];
+    if (f.label == -1) {
+      cfg.default_present = 1;
+      cfg.default_conf = f.confidence;
+      cfg.default_area = f.area;
+      cfg.default_has_zone_list = f.has_zone_list ? 1 : 0;
+      cfg.default_zone_bits = f.zone_bits;
+      continue;
+    }
+    REQUIRE(f.label >= 0 && f.label < WB_MAX_LABELS, "filter label out of range (0..127)");
+    cfg.present[f.label] = 1;
+    cfg.conf[f.label] = f.confidence;
+    cfg.area[f.label] = f.area;
+    cfg.has_zone_list[f.label] = f.has_zone_list ? 1 : 0;
+    cfg.zone_bits[f.label] = f.zone_bits;
+  }
+  if (c->cam_sat[cam]) {
+    CK(cudaFree(c->cam_sat[cam]));
+    c->cam_sat[cam] = nullptr;
+  }
+  if (n_zones > 0) {
+    size_t sat_elems = (size_t)n_zones * (height + 1) * (width + 1);
+    CK(cudaMalloc(&c->cam_sat[cam], sat_elems * sizeof(int32_t)));
+    uint8_t* d_r = nullptr;
+    size_t rb = (size_t)n_zones * height * width;
+    CK(cudaMalloc(&d_r, rb));
+    CK(cudaMemcpy(d_r, raster, rb, cudaMemcpyHostToDevice));
+    int lcnt = 0;
+    LaunchCtx lc{c->slots[0].stream, &lcnt};
+    launch_build_sat(lc, d_r, n_zones, height, width, c->cam_sat[cam]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->slots[0].stream));
+    CK(cudaFree(d_r));
+    cfg.sat = c->cam_sat[cam];
+  }
+  c->h_cams[cam] = cfg;
+  CK(cudaMemcpy(c->d_cams + cam, &cfg, sizeof(cfg), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int wb_register_host(wb_ctx* c, void* ptr, size_t bytes) {
+  REQUIRE(c && ptr && bytes, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  c->registered.push_back(ptr);
+  return 0;
+}
+int wb_unregister_host(wb_ctx* c, void* ptr) {
+  REQUIRE(c && ptr, "NULL argument");
+  for (size_t i = 0; i < c->registered.size(); ++i)
+    if (c->registered[i] == ptr) {
+      CK(cudaHostUnregister(ptr));
+      c->registered.erase(c->registered.begin() + i);
+      return 0;
+    }
+  return fail("pointer was not registered");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// the layer program.  `pre` != NULL feeds an already pre-processed input (wb_backbone); otherwise the
+// fused stem samples the frames directly.  When `times` is given every launch is bracketed by events.
+template <typename T>
+static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* pre, int first_layer,
+                      int last_layer) {
+  LaunchCtx lc{st, &s.launches};
+  T* arena = static_cast<T*>(s.arena);
+  const int NA = c->hdr.num_anchors, C1 = c->hdr.num_classes + 1;
+  const size_t end = last_layer < 0 ? c->layers.size() : (size_t)last_layer + 1;
+  for (size_t li = (size_t)first_layer; li < end; ++li) {
+    const wb_layer& L = c->layers[li];
+    const T* in = arena + (size_t)L.in_off * n;
+    const T* in2 = arena + (size_t)L.in2_off * n;
+    T* outp = arena + (size_t)L.out_off * n;
+    const float* w = L.w_tensor >= 0 ? c->tensor(L.w_tensor) : nullptr;
+    const float* sc = L.scale_tensor >= 0 ? c->tensor(L.scale_tensor) : nullptr;
+    const float* of = L.offset_tensor >= 0 ? c->tensor(L.offset_tensor) : nullptr;
+    switch (L.op) {
+      case WB_OP_STEM:
+        launch_stem<T>(lc, s.d_desc, pre, n, L, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub, w,
+                       sc, of, outp);
+        break;
+      case WB_OP_DW:
+        launch_dw<T>(lc, n, L, in, w, sc, of, outp);
+        break;
+      case WB_OP_ADD:
+        launch_add<T>(lc, (size_t)n * L.out_h * L.out_w * L.out_c, in, in2, outp);
+        break;
+      case WB_OP_PW:
+      case WB_OP_CONV:
+      case WB_OP_HEAD:
+        if (sizeof(T) == 4) {
+          launch_gemm_f32(lc, n, L, reinterpret_cast<const float*>(in), w, sc, of, reinterpret_cast<float*>(outp),
+                          s.d_enc, s.d_logits, NA, C1);
+        } else {
+          std::string err;
+          if (tc_launch_gemm(lc, c->tc, (int)li, n, L, reinterpret_cast<const __nv_bfloat16*>(in), sc, of,
+                             reinterpret_cast<__nv_bfloat16*>(outp), s.d_enc, s.d_logits, NA, C1, &err))
+            return fail("layer " + std::string(L.name) + ": " + err);
+        }
+        break;
+      default:
+        return fail("unknown layer op " + std::to_string(L.op));
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int run_post(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t flags) {
+  LaunchCtx lc{st, &s.launches};
+  float* rb = s.d_raw;
+  float* rs = rb + (size_t)c->max_batch * WB_MAX_DETECTIONS * 4;
+  float* rc = rs + (size_t)c->max_batch * WB_MAX_DETECTIONS;
+  launch_post(lc, n, c->pp, s.d_enc, s.d_logits, c->tensor(c->hdr.anchors_tensor), s.d_desc, c->d_cams, flags,
+              s.d_dec, s.d_cand_count, s.d_cand, s.d_sel_count, s.d_sel, s.d_out, s.d_verdicts, rb, rs, rc,
+              s.d_raw_num);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int run_all(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t flags) {
+  int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, 0, -1)
+                             : run_layers<float>(c, s, st, n, nullptr, 0, -1);
+  if (rc) return rc;
+  return run_post(c, s, st, n, flags);
+}
+
+// kernels of one batch, through a CUDA graph when possible (launch-bound at small batch)
+static int enqueue_kernels(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t flags) {
+  const uint32_t gflags = flags & WB_F_FUSE_FILTERS;
+  if (!c->use_graph) {
+    s.launches = 0;
+    return run_all(c, s, st, n, gflags);
+  }
+  if (s.graph_exec == nullptr || s.graph_n != n || s.graph_flags != gflags) {
+    if (s.graph_exec) {
+      cudaGraphExecDestroy(s.graph_exec);
+      s.graph_exec = nullptr;
+    }
+    // warm-up run outside capture (sets function attributes, validates launches)
+    s.launches = 0;
+    if (int rc = run_all(c, s, st, n, gflags)) return rc;
+    CK(cudaStreamSynchronize(st));
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    s.launches = 0;
+    int rc = run_all(c, s, st, n, gflags);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&s.graph_exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    s.graph_n = n;
+    s.graph_flags = gflags;
+  }
+  CK(cudaGraphLaunch(s.graph_exec, st));
+  return 0;
+}
+
+static int fill_desc(wb_ctx* c, Slot& s, int n, const uint8_t* const* frames, const int32_t* cam_ids,
+                     bool on_device, cudaStream_t st) {
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    int cam = cam_ids[i];
+    REQUIRE(cam >= 0 && cam < WB_MAX_CAMERAS && c->h_cams[cam].width > 0,
+            "cam_id " + std::to_string(cam) + " has not been configured with wb_set_camera");
+    REQUIRE(frames == nullptr || frames[i] != nullptr, "NULL frame pointer");
+    total += ((size_t)c->h_cams[cam].width * c->h_cams[cam].height * 3 + 255) / 256 * 256;
+  }
+  if (!on_device && frames != nullptr && total > s.d_frames_cap) {
+    CK(cudaStreamSynchronize(st));
+    if (s.d_frames) CK(cudaFree(s.d_frames));
+    s.d_frames_cap = total + total / 4;
+    CK(cudaMalloc(&s.d_frames, s.d_frames_cap));
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    const CameraCfg& cc = c->h_cams[cam_ids[i]];
+    size_t bytes = (size_t)cc.width * cc.height * 3;
+    FrameDesc d;
+    d.w = cc.width;
+    d.h = cc.height;
+    d.cam = cam_ids[i];
+    d._pad = 0;
+    if (frames == nullptr) {
+      d.ptr = nullptr;
+    } else if (on_device) {
+      d.ptr = frames[i];
+    } else {
+      d.ptr = s.d_frames + off;
+      CK(cudaMemcpyAsync(s.d_frames + off, frames[i], bytes, cudaMemcpyHostToDevice, st));
+      off += (bytes + 255) / 256 * 256;
+    }
+    s.h_desc[i] = d;
+  }
+  CK(cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+extern "C" {
+
+int wb_submit(wb_ctx* c, int slot, int n, const uint8_t* const* frames, const int32_t* cam_ids, uint32_t flags) {
+  REQUIRE(c && frames && cam_ids, "NULL argument");
+  REQUIRE(slot >= 0 && slot < WB_SLOTS, "slot out of range");
+  REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range (1..max_batch)");
+  Slot& s = c->slots[slot];
+  REQUIRE(!s.busy, "slot is busy: collect it first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream_of(slot);
+  CK(cudaEventRecord(s.ev0, st));
+  if (int rc = fill_desc(c, s, n, frames, cam_ids, (flags & WB_F_FRAMES_ON_DEVICE) != 0, st)) return rc;
+  if (int rc = enqueue_kernels(c, s, st, n, flags)) return rc;
+  if (!(flags & WB_F_OUT_ON_DEVICE)) {
+    CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(wb_detection) * (size_t)n * WB_MAX_DETECTIONS,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_verdicts, s.d_verdicts, sizeof(uint32_t) * (size_t)n * WB_MAX_DETECTIONS,
+                       cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(s.ev1, st));
+  s.n = n;
+  s.flags = flags;
+  s.busy = true;
+  c->last_launches = s.launches;
+  return 0;
+}
+
+int wb_collect(wb_ctx* c, int slot, wb_detection* const* out, uint32_t* const* verdicts, float* gpu_ms) {
+  REQUIRE(c, "NULL ctx");
+  REQUIRE(slot >= 0 && slot < WB_SLOTS, "slot out of range");
+  Slot& s = c->slots[slot];
+  REQUIRE(s.busy, "slot has no batch in flight");
+  CK(cudaSetDevice(c->device));
+  s.busy = false;
+  CK(cudaEventSynchronize(s.ev1));
+  if (gpu_ms) CK(cudaEventElapsedTime(gpu_ms, s.ev0, s.ev1));
+  if (s.flags & WB_F_OUT_ON_DEVICE) {
+    cudaStream_t st = c->stream_of(slot);
+    for (int i = 0; i < s.n; ++i) {
+      if (out && out[i])
+        CK(cudaMemcpyAsync(out[i], s.d_out + (size_t)i * WB_MAX_DETECTIONS, sizeof(wb_detection) * WB_MAX_DETECTIONS,
+                           cudaMemcpyDeviceToDevice, st));
+      if (verdicts && verdicts[i])
+        CK(cudaMemcpyAsync(verdicts[i], s.d_verdicts + (size_t)i * WB_MAX_DETECTIONS,
+                           sizeof(uint32_t) * WB_MAX_DETECTIONS, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  for (int i = 0; i < s.n; ++i) {
+    if (out && out[i])
+      memcpy(out[i], s.h_out + (size_t)i * WB_MAX_DETECTIONS, sizeof(wb_detection) * WB_MAX_DETECTIONS);
+    if (verdicts && verdicts[i])
+      memcpy(verdicts[i], s.h_verdicts + (size_t)i * WB_MAX_DETECTIONS, sizeof(uint32_t) * WB_MAX_DETECTIONS);
+  }
+  return 0;
+}
+
+int wb_detect(wb_ctx* c, int n, const uint8_t* const* frames, const int32_t* cam_ids, uint32_t flags,
+              wb_detection* const* out, uint32_t* const* verdicts, float* gpu_ms) {
+  if (int rc = wb_submit(c, 0, n, frames, cam_ids, flags)) return rc;
+  return wb_collect(c, 0, out, verdicts, gpu_ms);
+}
+
+// ---------------------------------------------------------------------------------------------------
+int wb_preprocess(wb_ctx* c, int n, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights,
+                  float* out) {
+  REQUIRE(c && frames && widths && heights && out, "NULL argument");
+  REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  CK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  REQUIRE(!s.busy, "slot 0 is busy");
+  cudaStream_t st = c->stream_of(0);
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += (size_t)widths[i] * heights[i] * 3;
+  if (total > s.d_frames_cap) {
+    if (s.d_frames) CK(cudaFree(s.d_frames));
+    s.d_frames_cap = total;
+    CK(cudaMalloc(&s.d_frames, total));
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    size_t bytes = (size_t)widths[i] * heights[i] * 3;
+    CK(cudaMemcpyAsync(s.d_frames + off, frames[i], bytes, cudaMemcpyHostToDevice, st));
+    s.h_desc[i] = FrameDesc{s.d_frames + off, widths[i], heights[i], -1, 0};
+    off += bytes;
+  }
+  CK(cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, st));
+  LaunchCtx lc{st, &s.launches};
+  launch_preprocess_f32(lc, s.d_desc, n, s.d_pre, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, s.d_pre, sizeof(float) * (size_t)n * c->hdr.input_h * c->hdr.input_w * 3,
+                     cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int wb_backbone(wb_ctx* c, int n, const float* pre, float* enc, float* logits, int stop_layer, float* layer_out,
+                size_t layer_out_floats) {
+  REQUIRE(c && pre, "NULL argument");
+  REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  REQUIRE(stop_layer < (int)c->layers.size(), "stop_layer out of range");
+  CK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  REQUIRE(!s.busy, "slot 0 is busy");
+  cudaStream_t st = c->stream_of(0);
+  const size_t pre_floats = (size_t)n * c->hdr.input_h * c->hdr.input_w * 3;
+  CK(cudaMemcpyAsync(s.d_pre, pre, sizeof(float) * pre_floats, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(s.d_enc, 0, sizeof(float) * (size_t)n * c->hdr.num_anchors * 4, st));
+  CK(cudaMemsetAsync(s.d_logits, 0, sizeof(float) * (size_t)n * c->hdr.num_anchors * (c->hdr.num_classes + 1), st));
+  s.launches = 0;
+  int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, s.d_pre, 0, stop_layer)
+                             : run_layers<float>(c, s, st, n, s.d_pre, 0, stop_layer);
+  if (rc) return rc;
+  if (enc) CK(cudaMemcpyAsync(enc, s.d_enc, sizeof(float) * (size_t)n * c->hdr.num_anchors * 4, cudaMemcpyDeviceToHost, st));
+  if (logits)
+    CK(cudaMemcpyAsync(logits, s.d_logits, sizeof(float) * (size_t)n * c->hdr.num_anchors * (c->hdr.num_classes + 1),
+                       cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stop_layer >= 0 && layer_out) {
+    const wb_layer& L = c->layers[stop_layer];
+    REQUIRE(L.op != WB_OP_HEAD, "head layers have no activation output");
+    size_t elems = (size_t)n * L.out_h * L.out_w * L.out_c;
+    REQUIRE(layer_out_floats >= elems, "layer_out too small");
+    if (c->precision == 0) {
+      CK(cudaMemcpy(layer_out, static_cast<float*>(s.arena) + (size_t)L.out_off * n, elems * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<uint16_t> tmp(elems);
+      CK(cudaMemcpy(tmp.data(), static_cast<uint16_t*>(s.arena) + (size_t)L.out_off * n, elems * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < elems; ++i) {
+        uint32_t u = (uint32_t)tmp[i] << 16;
+        memcpy(&layer_out[i], &u, 4);
+      }
+    }
+  }
+  c->last_launches = s.launches;
+  return 0;
+}
+
+int wb_postprocess(wb_ctx* c, int n, const float* enc, const float* logits, const int32_t* cam_ids, uint32_t flags,
+                   wb_detection* const* out, uint32_t* const* verdicts, float* boxes, float* scores, float* classes,
+                   int32_t* num) {
+  REQUIRE(c && enc && logits && cam_ids, "NULL argument");
+  REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  CK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  REQUIRE(!s.busy, "slot 0 is busy");
+  cudaStream_t st = c->stream_of(0);
+  const int NA = c->hdr.num_anchors, C1 = c->hdr.num_classes + 1;
+  CK(cudaMemcpyAsync(s.d_enc, enc, sizeof(float) * (size_t)n * NA * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.d_logits, logits, sizeof(float) * (size_t)n * NA * C1, cudaMemcpyHostToDevice, st));
+  if (int rc = fill_desc(c, s, n, nullptr, cam_ids, false, st)) return rc;
+  s.launches = 0;
+  if (int rc = run_post(c, s, st, n, flags)) return rc;
+  const size_t B = c->max_batch;
+  CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(wb_detection) * (size_t)n * WB_MAX_DETECTIONS, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(s.h_verdicts, s.d_verdicts, sizeof(uint32_t) * (size_t)n * WB_MAX_DETECTIONS, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(s.h_raw, s.d_raw, sizeof(float) * B * WB_MAX_DETECTIONS * 6, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(s.h_raw_num, s.d_raw_num, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    if (out && out[i]) memcpy(out[i], s.h_out + (size_t)i * WB_MAX_DETECTIONS, sizeof(wb_detection) * WB_MAX_DETECTIONS);
+    if (verdicts && verdicts[i])
+      memcpy(verdicts[i], s.h_verdicts + (size_t)i * WB_MAX_DETECTIONS, sizeof(uint32_t) * WB_MAX_DETECTIONS);
+  }
+  if (boxes) memcpy(boxes, s.h_raw, sizeof(float) * (size_t)n * WB_MAX_DETECTIONS * 4);
+  if (scores) memcpy(scores, s.h_raw + B * WB_MAX_DETECTIONS * 4, sizeof(float) * (size_t)n * WB_MAX_DETECTIONS);
+  if (classes) memcpy(classes, s.h_raw + B * WB_MAX_DETECTIONS * 5, sizeof(float) * (size_t)n * WB_MAX_DETECTIONS);
+  if (num) memcpy(num, s.h_raw_num, sizeof(int) * n);
+  c->last_launches = s.launches;
+  return 0;
+}
+
+int wb_filter_rows(wb_ctx* c, int cam, int n_rows, wb_detection* rows, uint32_t* verdicts) {
+  REQUIRE(c && rows && verdicts, "NULL argument");
+  REQUIRE(cam >= 0 && cam < WB_MAX_CAMERAS && c->h_cams[cam].width > 0, "camera has not been configured");
+  REQUIRE(n_rows >= 1 && n_rows <= WB_MAX_DETECTIONS * c->max_batch, "n_rows out of range");
+  CK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  REQUIRE(!s.busy, "slot 0 is busy");
+  cudaStream_t st = c->stream_of(0);
+  CK(cudaMemcpyAsync(s.d_out, rows, sizeof(wb_detection) * n_rows, cudaMemcpyHostToDevice, st));
+  LaunchCtx lc{st, &s.launches};
+  launch_filter_rows(lc, c->d_cams + cam, n_rows, s.d_out, s.d_verdicts);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rows, s.d_out, sizeof(wb_detection) * n_rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(verdicts, s.d_verdicts, sizeof(uint32_t) * n_rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int wb_last_launch_count(wb_ctx* c, int* launches) {
+  REQUIRE(c && launches, "NULL argument");
+  *launches = c->last_launches;
+  return 0;
+}
+
+// runs the program once, un-graphed, with an event pair around every layer and one around the post
+// stage: per-layer device times for bench.py's roofline (kinds[i] = layer op, 100 = post stage)
+int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, const int32_t* cam_ids,
+                      float* ms, int32_t* kinds, int max_launches, int* n_out) {
+  REQUIRE(c && device_frames && cam_ids && ms && kinds && n_out, "NULL argument");
+  REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  CK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  REQUIRE(!s.busy, "slot 0 is busy");
+  cudaStream_t st = c->stream_of(0);
+  if (int rc = fill_desc(c, s, n, device_frames, cam_ids, true, st)) return rc;
+  const int nl = (int)c->layers.size();
+  REQUIRE(max_launches >= nl + 1, "max_launches too small");
+  std::vector<cudaEvent_t> ev(nl + 2);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  s.launches = 0;
+  CK(cudaEventRecord(ev[0], st));
+  for (int li = 0; li < nl; ++li) {
+    int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, li, li)
+                               : run_layers<float>(c, s, st, n, nullptr, li, li);
+    if (rc) return rc;
+    CK(cudaEventRecord(ev[li + 1], st));
+    kinds[li] = (int)c->layers[li].op;
+  }
+  if (int rc = run_post(c, s, st, n, 0)) return rc;
+  CK(cudaEventRecord(ev[nl + 1], st));
+  CK(cudaEventSynchronize(ev[nl + 1]));
+  for (int li = 0; li <= nl; ++li) CK(cudaEventElapsedTime(&ms[li], ev[li], ev[li + 1]));
+  kinds[nl] = 100;
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_out = nl + 1;
+  c->last_launches = s.launches;
+  return 0;
+}
+
+}  // extern "C"
