@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 echo "== pytest -m gpu" 
-timeout 900 python -m pytest tests -m gpu -q -x --timeout=600 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q --timeout=600 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee gpurun_out/smoke.log
 echo "== bench"

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ST_TY* ST_TX)
   const int K = L.kh, S = L.stride;
   const int tile_h = (ST_TY - 1) * S + K, tile_w = (ST_TX - 1) * S + K;
   float* s_in = smem;                              // [tile_h][tile_w][3]
-  float* s_w = smem + tile_h * tile_w * 3;         // [K*K*3][n_pad]
+  float* s_w = smem + ((tile_h * tile_w * 3 + 3) & ~3);  // [K*K*3][n_pad], 16-byte aligned
   const int f = blockIdx.z;
   const int oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
   const int tid = threadIdx.x;
@@ -172,7 +172,7 @@ void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre,
                  int in_h, int in_w, float mul, float sub, const float* w, const float* scale,
                  const float* offset, T* out) {
   const int tile_h = (ST_TY - 1) * L.stride + L.kh, tile_w = (ST_TX - 1) * L.stride + L.kw;
-  size_t smem = ((size_t)tile_h * tile_w * 3 + (size_t)L.kh * L.kw * 3 * L.n_pad) * sizeof(float);
+  size_t smem = ((((size_t)tile_h * tile_w * 3 + 3) & ~(size_t)3) + (size_t)L.kh * L.kw * 3 * L.n_pad) * sizeof(float);
   dim3 grid((L.out_w + ST_TX - 1) / ST_TX, (L.out_h + ST_TY - 1) / ST_TY, n);
   static bool attr_done = false;
   if (!attr_done && smem > 48 * 1024) {
