@@ -14,9 +14,10 @@ from watsor_b200.stream.share import Detection, FrameBuffer
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module')
-def detector(shapes_model):
-    with B200ObjectDetector(None, device=0, max_batch=64, precision=0, model_blob=shapes_model.to_blob()) as d:
+@pytest.fixture(scope='module', params=[0, 2], ids=['fp32-cuda-cores', 'fp32-3xtf32-tcgen05'])
+def detector(shapes_model, request):
+    with B200ObjectDetector(None, device=0, max_batch=64, precision=request.param,
+                            model_blob=shapes_model.to_blob()) as d:
         yield d
 
 

@@ -10,9 +10,9 @@ from watsor_b200.model import OP_ADD, OP_HEAD
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module')
-def engine(shapes_model):
-    with Engine(shapes_model.to_blob(), device=0, max_batch=8, precision=0) as e:
+@pytest.fixture(scope='module', params=[0, 2], ids=['fp32-cuda-cores', 'fp32-3xtf32-tcgen05'])
+def engine(shapes_model, request):
+    with Engine(shapes_model.to_blob(), device=0, max_batch=8, precision=request.param) as e:
         yield e
 
 
@@ -55,9 +55,9 @@ def test_backbone_layer_by_layer(engine, shapes_model, shapes_oracle):
         err = np.abs(got[0] - want).max()
         scale = max(1.0, float(np.abs(want).max()))
         worst = max(worst, err / scale)
-        assert err <= 2e-5 * scale, (li, layer.name, err, scale)
+        assert err <= 6e-5 * scale, (li, layer.name, err, scale)
     genc, glg, _ = engine.backbone(pre[None])
-    assert np.abs(genc[0] - enc).max() <= 5e-5 and np.abs(glg[0] - lg).max() <= 5e-5
+    assert np.abs(genc[0] - enc).max() <= 1e-4 and np.abs(glg[0] - lg).max() <= 3e-4
     print('worst relative layer error %.2e' % worst)
 
 

@@ -95,9 +95,10 @@ void launch_dw(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const
                const float* offset, T* out);
 template <typename T>
 void launch_add(const LaunchCtx& lc, size_t elems, const T* a, const T* b, T* out);
-void launch_gemm_f32(const LaunchCtx& lc, int n, const wb_layer& L, const float* in, const float* w,
-                     const float* scale, const float* offset, float* out, float* enc, float* logits,
-                     int num_anchors, int num_classes_p1);
+template <typename T>
+void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w,
+                    const float* scale, const float* offset, T* out, float* enc, float* logits,
+                    int num_anchors, int num_classes_p1);
 void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* enc, const float* logits,
                  const float* anchors, const FrameDesc* frames, const CameraCfg* cams, uint32_t flags,
                  float* dec_boxes, int* cand_count, unsigned long long* cand, int* sel_count,

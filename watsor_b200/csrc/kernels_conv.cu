@@ -86,12 +86,13 @@ template void launch_add<__nv_bfloat16>(const LaunchCtx&, size_t, const __nv_bfl
 //   K never straddles a filter tap because in_c % 16 == 0).
 //   Head layers scatter their columns straight into the concatenated [n][anchors][4] /
 //   [n][anchors][C+1] tensors (graph nodes `concat`, `concat_1`).
+template <typename T>
 struct GemmArgs {
-  const float* in;
+  const T* in;
   const float* w;
   const float* scale;
   const float* offset;
-  float* out;
+  T* out;
   float* enc;
   float* logits;
   int M, N, K, ldw;
@@ -100,8 +101,8 @@ struct GemmArgs {
   int is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
+template <typename T, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
   constexpr int BK = 16;
   constexpr int NT = 256;
   static_assert((BM / TM) * (BN / TN) == NT, "thread tiling");
@@ -149,14 +150,13 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a_ok[i]) {
         if (!im2col) {
-          v = __ldg(reinterpret_cast<const float4*>(g.in + (size_t)(m0 + a_row[i]) * g.K + k0 + a_kq[i] * 4));
+          v = ActIO<T>::ld4(g.in + (size_t)(m0 + a_row[i]) * g.K + k0 + a_kq[i] * 4);
         } else {
           int tap = k0 / g.in_c, ci = k0 - tap * g.in_c;
           int ky = tap / g.kw, kx = tap - ky * g.kw;
           int iy = a_oy[i] * g.stride - g.pad_t + ky, ix = a_ox[i] * g.stride - g.pad_l + kx;
           if (iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w)
-            v = __ldg(reinterpret_cast<const float4*>(
-                g.in + (((size_t)a_f[i] * g.in_h + iy) * g.in_w + ix) * g.in_c + ci + a_kq[i] * 4));
+            v = ActIO<T>::ld4(g.in + (((size_t)a_f[i] * g.in_h + iy) * g.in_w + ix) * g.in_c + ci + a_kq[i] * 4);
         }
       }
       a_reg[i] = v;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
           v[jj] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
         }
         if (!g.is_head) {
-          *reinterpret_cast<float4*>(g.out + (size_t)m * g.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+          ActIO<T>::st4(g.out + (size_t)m * g.N + n, make_float4(v[0], v[1], v[2], v[3]));
         } else {
           const int hw = g.out_h * g.out_w;
           const int f = m / hw, p = m - f * hw;
@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
     }
 }
 
-void launch_gemm_f32(const LaunchCtx& lc, int n, const wb_layer& L, const float* in, const float* w,
-                     const float* scale, const float* offset, float* out, float* enc, float* logits,
-                     int num_anchors, int num_classes_p1) {
-  GemmArgs g;
+template <typename T>
+void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w,
+                    const float* scale, const float* offset, T* out, float* enc, float* logits,
+                    int num_anchors, int num_classes_p1) {
+  GemmArgs<T> g;
   g.in = in;
   g.w = w;
   g.scale = scale;
@@ -304,10 +305,14 @@ void launch_gemm_f32(const LaunchCtx& lc, int n, const wb_layer& L, const float*
   long big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128);
   if (big >= 148 && g.N >= 128) {
     dim3 grid((g.N + 127) / 128, (g.M + 127) / 128);
-    k_gemm_f32<128, 128, 8, 8><<<grid, 256, 0, lc.stream>>>(g);
+    k_gemm_cc<T, 128, 128, 8, 8><<<grid, 256, 0, lc.stream>>>(g);
   } else {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-    k_gemm_f32<64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g);
+    k_gemm_cc<T, 64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g);
   }
   ++*lc.launch_counter;
 }
+template void launch_gemm_cc<float>(const LaunchCtx&, int, const wb_layer&, const float*, const float*, const float*,
+                                    const float*, float*, float*, float*, int, int);
+template void launch_gemm_cc<__nv_bfloat16>(const LaunchCtx&, int, const wb_layer&, const __nv_bfloat16*, const float*,
+                                            const float*, const float*, __nv_bfloat16*, float*, float*, int, int);

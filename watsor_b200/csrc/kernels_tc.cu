@@ -1,14 +1,525 @@
-// kernels_tc.cu -- placeholder until the tcgen05 GEMM lands (precision 1 is refused loudly).
+// kernels_tc.cu -- tensor-core path for the dense 1x1 convolutions and heads (K4/K6):
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma with the accumulator in
+// TMEM -> tcgen05.ld epilogue (folded BatchNorm / bias, ReLU6) -> global.  sm_100a only.
+//
+// Two operand modes share one warp-specialised kernel:
+//   TC_BF16    A, W in bf16 (kind::f16), bf16 activations out            -- "fast" mode
+//   TC_TF32X3  A, W in fp32, every product formed as three TF32 MMAs
+//              (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate)      -- fp32-faithful "parity" mode
+// In TF32X3 the activation tile lands in shared memory as raw fp32; converter warps split it in place
+// into hi = a & 0xffffe000 and lo = (a - hi) & 0xffffe000 (both exactly representable in TF32, so
+// the tensor core's own input rounding never matters); the weights are split once on the host.
+//
+// Warp roles (192 + 128*X3 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2..5 epilogue (TMEM lane quarter = warp_idx % 4), warps 6..9 converters (TF32X3 only).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "kernels_tc.cuh"
 
-int tc_prepare_weights(const std::vector<wb_layer>&, const std::vector<wb_tensor_entry>&, const float*, TcWeights*,
-                       std::string* err) {
-  *err = "the bf16 tcgen05 path is not built into this library";
-  return 1;
+namespace {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-void tc_free_weights(TcWeights*) {}
-int tc_launch_gemm(const LaunchCtx&, const TcWeights&, int, int, const wb_layer&, const __nv_bfloat16*, const float*,
-                   const float*, __nv_bfloat16*, float*, float*, int, int, std::string* err) {
-  *err = "the bf16 tcgen05 path is not built into this library";
-  return 1;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (TF32)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64).
+// Rows are 128 B apart, 8-row swizzle atoms 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, K-major both, N>>3, M>>4
+__host__ __device__ inline uint32_t make_idesc(bool tf32, int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format = F32
+  d |= (tf32 ? 2u : 1u) << 7;          // a_format  (BF16 = 1, TF32 = 2)
+  d |= (tf32 ? 2u : 1u) << 10;         // b_format
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+
+constexpr int BLOCK_M = 128;
+constexpr int ROW_BYTES = 128;                     // one swizzle row = 64 bf16 or 32 fp32 along K
+constexpr int A_TILE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
+constexpr int UMMA_K_BYTES = 32;
+
+struct TcArgs {
+  const float* scale;
+  const float* offset;
+  void* out;  // bf16 or fp32 [M][N]
+  float* enc;
+  float* logits;
+  int M, N, n_pad, K;  // K in elements
+  int block_n, stages, k_blocks;
+  int n_main;  // TF32X3: the hi*hi products rotate over n_main TMEM accumulators (+1 for the corrections)
+  int act, is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1, hw;
+};
+
+// MODE 0: bf16 operands; MODE 1: tf32 single product (diagnostic); MODE 2: tf32 x3 split
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
+    k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
+  constexpr bool TF32 = MODE != 0;
+  constexpr bool X3 = MODE == 2;
+  constexpr int ELEM = TF32 ? 4 : 2;
+  constexpr int K_PER_BLOCK = ROW_BYTES / ELEM;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = g.block_n * ROW_BYTES;
+  const int stage_bytes = A_TILE_BYTES * (X3 ? 2 : 1) + b_tile_bytes * (X3 ? 2 : 1);
+  uint8_t* bar_base = smem + (size_t)g.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);          // TMA landed
+  uint64_t* empty = full + g.stages;                               // MMAs done with the stage
+  uint64_t* conv = empty + g.stages;                               // converters done (X3)
+  uint64_t* acc_full = conv + g.stages;                            // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * g.block_n;
+  // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
+  const int n_acc = X3 ? g.n_main + 1 : 1;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < g.block_n * n_acc) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&conv[s]), 4);  // one arrive per converter warp
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < g.k_blocks; ++kb) {
+        const int s = kb % g.stages;
+        const uint32_t ph = (kb / g.stages) & 1;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const uint32_t bar = smem_u32(&full[s]);
+        mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
+        tma_load_2d(smem_u32(st), &map_a, bar, kb * K_PER_BLOCK, m0);
+        uint8_t* sb = st + A_TILE_BYTES * (X3 ? 2 : 1);
+        tma_load_2d(smem_u32(sb), &map_b, bar, kb * K_PER_BLOCK, n0);
+        if (X3) tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bar, kb * K_PER_BLOCK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(TF32, BLOCK_M, g.block_n);
+    for (int kb = 0; kb < g.k_blocks; ++kb) {
+      const int s = kb % g.stages;
+      const uint32_t ph = (kb / g.stages) & 1;
+      mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * (X3 ? 2 : 1)), b_lo = b_hi + b_tile_bytes;
+        // The tensor core adds into the fp32 accumulator with truncation (round toward zero), a bias
+        // that grows with the length of the accumulation chain.  TF32X3 therefore rotates the dominant
+        // hi*hi products over n_main accumulators and keeps the two small correction products in a
+        // separate one; the epilogue adds the partial sums with round-to-nearest.
+#pragma unroll
+        for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+          const uint32_t koff = k * UMMA_K_BYTES;
+          const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+          if (!X3) {
+            umma<TF32>(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+          } else {
+            const uint32_t d_main = tmem_base + (uint32_t)((step % g.n_main) * g.block_n);
+            const uint32_t d_corr = tmem_base + (uint32_t)(g.n_main * g.block_n);
+            umma<TF32>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
+            umma<TF32>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+            umma<TF32>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&empty[s]));
+        if (kb == g.k_blocks - 1) umma_commit(smem_u32(acc_full));
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue (TMEM -> global)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(smem_u32(acc_full), 0);
+    tc_fence_after();
+    const int f = g.is_head ? m / g.hw : 0;
+    const size_t head_row = g.is_head ? (size_t)f * g.num_anchors + g.row_off + (size_t)(m - f * g.hw) * g.anchors_per_loc : 0;
+    for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (X3) {
+        const int used = min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES));
+        for (int a = 1; a <= g.n_main; ++a) {
+          if (a < g.n_main && a >= used) continue;  // accumulator never written (very small K)
+          uint32_t u[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * g.block_n + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])));
+        }
+      }
+      const int n = n0 + c0;
+      if (m >= g.M || n >= g.N) continue;
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int nn = n + j;
+        float s = nn < g.n_pad ? __ldg(g.scale + nn) : 1.f, o = nn < g.n_pad ? __ldg(g.offset + nn) : 0.f;
+        float x = affine_rn(__uint_as_float(v[j]), s, o);
+        y[j] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+      }
+      if (g.is_head) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int nn = n + j;
+          if (nn >= g.N) break;
+          if (nn < g.n_box)
+            g.enc[head_row * 4 + nn] = y[j];
+          else
+            g.logits[head_row * g.ncp1 + (nn - g.n_box)] = y[j];
+        }
+      } else if (TF32) {
+        float* o = reinterpret_cast<float*>(g.out) + (size_t)m * g.N + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          if (n + j < g.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)m * g.N + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8)
+          if (n + j < g.N) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[j], y[j + 1]), p1 = __floats2bfloat162_rn(y[j + 2], y[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[j + 4], y[j + 5]), p3 = __floats2bfloat162_rn(y[j + 6], y[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+      }
+    }
+  } else if (X3) {
+    // ------------------------------------------------------------------ converters (A -> hi / lo)
+    const int t = threadIdx.x - 192;  // 0..127
+    for (int kb = 0; kb < g.k_blocks; ++kb) {
+      const int s = kb % g.stages;
+      const uint32_t ph = (kb / g.stages) & 1;
+      mbar_wait(smem_u32(&full[s]), ph);
+      uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
+      uint4* lo = a + A_TILE_BYTES / 16;
+#pragma unroll 4
+      for (int i = t; i < A_TILE_BYTES / 16; i += 128) {
+        uint4 x = a[i], h, l;
+        h.x = x.x & 0xFFFFE000u;
+        h.y = x.y & 0xFFFFE000u;
+        h.z = x.z & 0xFFFFE000u;
+        h.w = x.w & 0xFFFFE000u;
+        l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(h.x))) & 0xFFFFE000u;
+        l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
+        l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
+        l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
+        a[i] = h;
+        lo[i] = l;
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&conv[s]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// -------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D K-major matrix [rows][k] -> tensor map with a (128 B x box_rows) box, 128B swizzle
+bool make_map(CUtensorMap* map, const void* base, int elem_bytes, int rows, int k, int box_rows, std::string* err) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return false;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem_bytes), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows " + std::to_string(rows) +
+           ", k " + std::to_string(k) + ", box_rows " + std::to_string(box_rows) + ")";
+    return false;
+  }
+  return true;
+}
+
+int pick_block_n(int n_pad) {
+  if (n_pad <= 128) return n_pad;            // multiples of 16 up to 128: one N tile
+  if (n_pad % 128 == 0) return 128;
+  if (n_pad % 96 == 0) return 96;
+  if (n_pad % 64 == 0) return 64;
+  if (n_pad % 48 == 0) return 48;
+  if (n_pad % 32 == 0) return 32;
+  return 16;
+}
+
+}  // namespace
+
+bool tc_layer_supported(const wb_layer& L) {
+  return (L.op == WB_OP_PW || L.op == WB_OP_HEAD) && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.in_c % 16 == 0;
+}
+
+int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb_tensor_entry>& tensors,
+                       const float* host_data, int mode, TcWeights* out, std::string* err) {
+  out->mode = mode;
+  out->layers.assign(layers.size(), TcLayerWeights{});
+  for (size_t li = 0; li < layers.size(); ++li) {
+    const wb_layer& L = layers[li];
+    if (!tc_layer_supported(L)) continue;
+    TcLayerWeights& w = out->layers[li];
+    const int K = L.in_c, NP = L.n_pad;
+    const float* src = host_data + tensors[L.w_tensor].offset;  // [K][NP]
+    w.k = K;
+    w.n_pad = NP;
+    w.block_n = pick_block_n(NP);
+    const int elem = mode == TC_BF16 ? 2 : 4;
+    const size_t bytes = (size_t)NP * K * elem;
+    std::vector<uint8_t> hi(bytes), lo(mode == TC_TF32X3 ? bytes : 0);
+    for (int n = 0; n < NP; ++n)
+      for (int k = 0; k < K; ++k) {
+        float v = src[(size_t)k * NP + n];
+        if (mode == TC_BF16) {
+          __nv_bfloat16 b = __float2bfloat16_rn(v);
+          memcpy(&hi[((size_t)n * K + k) * 2], &b, 2);
+        } else {
+          uint32_t u;
+          memcpy(&u, &v, 4);
+          uint32_t h = mode == TC_TF32X3 ? (u & 0xFFFFE000u) : u;
+          memcpy(&hi[((size_t)n * K + k) * 4], &h, 4);
+          if (mode == TC_TF32X3) {
+            float hf;
+            memcpy(&hf, &h, 4);
+            float lf = v - hf;
+            uint32_t l;
+            memcpy(&l, &lf, 4);
+            l &= 0xFFFFE000u;
+            memcpy(&lo[((size_t)n * K + k) * 4], &l, 4);
+          }
+        }
+      }
+    if (cudaMalloc(&w.w, bytes) != cudaSuccess || cudaMemcpy(w.w, hi.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = "cudaMalloc/cudaMemcpy of tensor-core weights failed";
+      return 1;
+    }
+    if (!make_map(reinterpret_cast<CUtensorMap*>(w.tmap_b), w.w, elem, NP, K, w.block_n, err)) return 1;
+    if (mode == TC_TF32X3) {
+      if (cudaMalloc(&w.w_lo, bytes) != cudaSuccess ||
+          cudaMemcpy(w.w_lo, lo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        *err = "cudaMalloc/cudaMemcpy of tensor-core weights failed";
+        return 1;
+      }
+      if (!make_map(reinterpret_cast<CUtensorMap*>(w.tmap_b_lo), w.w_lo, elem, NP, K, w.block_n, err)) return 1;
+    } else {
+      memcpy(w.tmap_b_lo, w.tmap_b, sizeof(w.tmap_b));
+    }
+    w.ready = true;
+  }
+  return 0;
+}
+
+void tc_free_weights(TcWeights* w) {
+  for (auto& l : w->layers) {
+    if (l.w) cudaFree(l.w);
+    if (l.w_lo) cudaFree(l.w_lo);
+  }
+  w->layers.clear();
+}
+
+int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L, const void* in,
+                   const float* scale, const float* offset, void* out, float* enc, float* logits, int num_anchors,
+                   int num_classes_p1, std::string* err) {
+  const TcLayerWeights& w = tw.layers[layer_index];
+  if (!w.ready) {
+    *err = "no tensor-core weights for this layer";
+    return 1;
+  }
+  const int mode = tw.mode;
+  const int elem = mode == TC_BF16 ? 2 : 4;
+  TcArgs g;
+  g.scale = scale;
+  g.offset = offset;
+  g.out = out;
+  g.enc = enc;
+  g.logits = logits;
+  g.M = n * L.out_h * L.out_w;
+  g.N = L.out_c;
+  g.n_pad = L.n_pad;
+  g.K = L.in_c;
+  g.block_n = w.block_n;
+  g.k_blocks = (g.K * elem + ROW_BYTES - 1) / ROW_BYTES;
+  g.act = L.act;
+  g.is_head = L.op == WB_OP_HEAD;
+  g.anchors_per_loc = L.anchors_per_loc;
+  g.row_off = L.row_off;
+  g.n_box = L.n_box;
+  g.num_anchors = num_anchors;
+  g.ncp1 = num_classes_p1;
+  g.hw = L.out_h * L.out_w;
+  const int x3 = mode == TC_TF32X3 ? 2 : 1;
+  g.n_main = 1;
+  if (mode == TC_TF32X3) g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
+  const int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > g.k_blocks) stages = g.k_blocks;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 8 * (3 * stages + 1) + 16;
+  CUtensorMap map_a;
+  if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) return 1;
+  CUtensorMap map_b, map_b_lo;
+  memcpy(&map_b, w.tmap_b, sizeof(map_b));
+  memcpy(&map_b_lo, w.tmap_b_lo, sizeof(map_b_lo));
+  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
+  static bool attr_done[3] = {false, false, false};
+  cudaError_t e = cudaSuccess;
+  if (mode == TC_BF16) {
+    if (!attr_done[0]) {
+      e = cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      attr_done[0] = true;
+    }
+    k_gemm_tc<0><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+  } else if (mode == TC_TF32X1) {
+    if (!attr_done[1]) {
+      e = cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      attr_done[1] = true;
+    }
+    k_gemm_tc<1><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+  } else {
+    if (!attr_done[2]) {
+      e = cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      attr_done[2] = true;
+    }
+    k_gemm_tc<2><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+  }
+  if (e != cudaSuccess) {
+    *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  ++*lc.launch_counter;
+  return 0;
 }

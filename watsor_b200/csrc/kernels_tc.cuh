@@ -1,23 +1,30 @@
-// kernels_tc.cuh -- bf16 tensor-core (tcgen05 + TMA + TMEM) GEMM path for the dense convolutions.
+// kernels_tc.cuh -- tensor-core (tcgen05 + TMA + TMEM) GEMM path for the dense 1x1 convolutions.
 #pragma once
 #include <string>
 #include <vector>
 
 #include "common.cuh"
 
+enum TcMode { TC_BF16 = 0, TC_TF32X1 = 1, TC_TF32X3 = 2 };
+
 struct TcLayerWeights {
-  __nv_bfloat16* w = nullptr;  // [n_pad][K] K-major bf16 (B operand of the UMMA), device
-  int n_pad = 0, k = 0;
-  void* tmap_b = nullptr;      // host copy of the CUtensorMap for the weights
+  void* w = nullptr;     // [n_pad][K] K-major (bf16, or fp32 "hi" part), device
+  void* w_lo = nullptr;  // fp32 "lo" part (TF32X3)
+  int n_pad = 0, k = 0, block_n = 0;
+  bool ready = false;
+  alignas(64) unsigned char tmap_b[128];     // CUtensorMap of w
+  alignas(64) unsigned char tmap_b_lo[128];  // CUtensorMap of w_lo
 };
 
 struct TcWeights {
-  std::vector<TcLayerWeights> layers;  // indexed by layer number (empty entries for non-GEMM layers)
+  int mode = TC_BF16;
+  std::vector<TcLayerWeights> layers;  // indexed by layer number (unset entries for non-GEMM layers)
 };
 
+bool tc_layer_supported(const wb_layer& L);
 int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb_tensor_entry>& tensors,
-                       const float* host_data, TcWeights* out, std::string* err);
+                       const float* host_data, int mode, TcWeights* out, std::string* err);
 void tc_free_weights(TcWeights* w);
-int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L,
-                   const __nv_bfloat16* in, const float* scale, const float* offset, __nv_bfloat16* out, float* enc,
-                   float* logits, int num_anchors, int num_classes_p1, std::string* err);
+int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L, const void* in,
+                   const float* scale, const float* offset, void* out, float* enc, float* logits, int num_anchors,
+                   int num_classes_p1, std::string* err);

@@ -131,7 +131,8 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   REQUIRE(out != nullptr && model_blob != nullptr, "NULL argument");
   REQUIRE(blob_bytes >= sizeof(wb_model_header), "model blob too small");
   REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch out of range");
-  REQUIRE(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor core)");
+  REQUIRE(precision >= 0 && precision <= 3,
+          "precision must be 0 (fp32 CUDA cores), 1 (bf16 tcgen05), 2 (fp32 via 3xTF32 tcgen05) or 3 (1xTF32, diagnostic)");
   CK(cudaSetDevice(device));
   wb_ctx* c = new wb_ctx();
   c->device = device;
@@ -170,9 +171,10 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   }
   CK(cudaMalloc(&c->d_weights, floats * sizeof(float)));
   CK(cudaMemcpy(c->d_weights, p, floats * sizeof(float), cudaMemcpyHostToDevice));
-  if (precision == 1) {
+  if (precision != 0) {
     std::string err;
-    if (tc_prepare_weights(c->layers, c->tensors, reinterpret_cast<const float*>(p), &c->tc, &err))
+    const int mode = precision == 1 ? TC_BF16 : (precision == 2 ? TC_TF32X3 : TC_TF32X1);
+    if (tc_prepare_weights(c->layers, c->tensors, reinterpret_cast<const float*>(p), mode, &c->tc, &err))
       return fail("tensor-core weight preparation: " + err);
   }
   c->pp.num_anchors = c->hdr.num_anchors;
@@ -240,7 +242,7 @@ int wb_destroy(wb_ctx* c) {
 int wb_device_name(wb_ctx* c, char* buf, size_t n) {
   REQUIRE(c && buf && n > 0, "NULL argument");
   snprintf(buf, n, "%s (cuda:%d, sm_%d%d, %s)", c->prop.name, c->device, c->prop.major, c->prop.minor,
-           c->precision == 1 ? "bf16 tcgen05" : "fp32");
+           c->precision == 1 ? "bf16 tcgen05" : (c->precision == 2 ? "fp32 3xTF32 tcgen05" : (c->precision == 3 ? "tf32 tcgen05" : "fp32")));
   return 0;
 }
 
@@ -380,14 +382,13 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
       case WB_OP_PW:
       case WB_OP_CONV:
       case WB_OP_HEAD:
-        if (sizeof(T) == 4) {
-          launch_gemm_f32(lc, n, L, reinterpret_cast<const float*>(in), w, sc, of, reinterpret_cast<float*>(outp),
-                          s.d_enc, s.d_logits, NA, C1);
-        } else {
+        if (c->precision != 0 && tc_layer_supported(L)) {
           std::string err;
-          if (tc_launch_gemm(lc, c->tc, (int)li, n, L, reinterpret_cast<const __nv_bfloat16*>(in), sc, of,
-                             reinterpret_cast<__nv_bfloat16*>(outp), s.d_enc, s.d_logits, NA, C1, &err))
+          if (tc_launch_gemm(lc, c->tc, (int)li, n, L, static_cast<const void*>(in), sc, of, static_cast<void*>(outp),
+                             s.d_enc, s.d_logits, NA, C1, &err))
             return fail("layer " + std::string(L.name) + ": " + err);
+        } else {
+          launch_gemm_cc<T>(lc, n, L, in, w, sc, of, outp, s.d_enc, s.d_logits, NA, C1);
         }
         break;
       default:
@@ -613,7 +614,7 @@ int wb_backbone(wb_ctx* c, int n, const float* pre, float* enc, float* logits, i
     REQUIRE(L.op != WB_OP_HEAD, "head layers have no activation output");
     size_t elems = (size_t)n * L.out_h * L.out_w * L.out_c;
     REQUIRE(layer_out_floats >= elems, "layer_out too small");
-    if (c->precision == 0) {
+    if (c->elem_size() == 4) {
       CK(cudaMemcpy(layer_out, static_cast<float*>(s.arena) + (size_t)L.out_off * n, elems * 4, cudaMemcpyDeviceToHost));
     } else {
       std::vector<uint16_t> tmp(elems);

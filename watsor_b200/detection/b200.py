@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 from .. import _lib
-from ..engine import PRECISION_BF16_TC, PRECISION_FP32, Engine
+from ..engine import PRECISION_BF16_TC, PRECISION_FP32, PRECISION_TF32X3, Engine
 from ..model import Model, compile_frozen_graph
 from ..stream.share import MAX_DETECTIONS, Detection
 
@@ -51,10 +51,11 @@ def load_model_blob(model_path):
 
 
 def default_precision():
-    """`WATSOR_B200_PRECISION=fp32|bf16` (the reference's analogous switch is
-    TRT_FLOAT_PRECISION, main_for_gpu.py:24)."""
-    v = os.environ.get('WATSOR_B200_PRECISION', 'fp32').lower()
-    return PRECISION_BF16_TC if v in ('bf16', '16', 'tc') else PRECISION_FP32
+    """`WATSOR_B200_PRECISION=fp32|tf32x3|bf16` (the reference's analogous switch is
+    TRT_FLOAT_PRECISION, main_for_gpu.py:24).  Default: fp32-faithful tensor-core mode."""
+    v = os.environ.get('WATSOR_B200_PRECISION', 'tf32x3').lower()
+    return {'fp32': PRECISION_FP32, '32': PRECISION_FP32, 'bf16': PRECISION_BF16_TC, '16': PRECISION_BF16_TC,
+            'tf32x3': PRECISION_TF32X3}.get(v, PRECISION_TF32X3)
 
 
 class B200ObjectDetector(object):

@@ -12,7 +12,8 @@ from . import _lib
 from ._lib import ClassFilter, check
 from .stream.share import MAX_DETECTIONS, Detection
 
-PRECISION_FP32, PRECISION_BF16_TC = 0, 1
+# 0: fp32 CUDA-core convs; 1: bf16 tcgen05; 2: fp32 storage, dense convs as 3xTF32 tcgen05 (fp32-faithful)
+PRECISION_FP32, PRECISION_BF16_TC, PRECISION_TF32X3 = 0, 1, 2
 
 
 def _ptr_array(ptrs):
