@@ -126,6 +126,12 @@ int wb_submit(wb_ctx* ctx, int slot, int n, const uint8_t* const* frames, const 
 int wb_collect(wb_ctx* ctx, int slot, wb_detection* const* out, uint32_t* const* verdicts,
                float* gpu_ms);
 
+/* order the library's internal slot streams against a caller stream (0 = legacy default stream):
+ * direction 0: every slot stream waits for the work already enqueued on `cuda_stream`;
+ * direction 1: `cuda_stream` waits for everything enqueued on the slot streams.
+ * Lets a caller bracket several in-flight wb_submit() batches with its own CUDA events. */
+int wb_stream_fence(wb_ctx* ctx, uint64_t cuda_stream, int direction);
+
 /* ---- stage-level entry points (parity tests call the same kernels stage by stage) -------------- */
 /* graph nodes Cast + Preprocessor/... : out = float32 [n][in_h][in_w][3] on the host */
 int wb_preprocess(wb_ctx* ctx, int n, const uint8_t* const* frames, const int32_t* widths,

@@ -548,6 +548,26 @@ int wb_collect(wb_ctx* c, int slot, wb_detection* const* out, uint32_t* const* v
   return 0;
 }
 
+int wb_stream_fence(wb_ctx* c, uint64_t stream, int direction) {
+  REQUIRE(c, "NULL ctx");
+  REQUIRE(direction == 0 || direction == 1, "direction must be 0 or 1");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if (direction == 0) {
+    CK(cudaEventRecord(ev, user));
+    for (auto& s : c->slots) CK(cudaStreamWaitEvent(s.stream, ev, 0));
+  } else {
+    for (auto& s : c->slots) {
+      CK(cudaEventRecord(ev, s.stream));
+      CK(cudaStreamWaitEvent(user, ev, 0));
+    }
+  }
+  CK(cudaEventDestroy(ev));
+  return 0;
+}
+
 int wb_detect(wb_ctx* c, int n, const uint8_t* const* frames, const int32_t* cam_ids, uint32_t flags,
               wb_detection* const* out, uint32_t* const* verdicts, float* gpu_ms) {
   if (int rc = wb_submit(c, 0, n, frames, cam_ids, flags)) return rc;

@@ -136,6 +136,10 @@ class Engine:
         check(self.lib.wb_collect(self._ctx, slot, op, vp, byref(ms)))
         return ms.value
 
+    def stream_fence(self, cuda_stream, direction):
+        """direction 0: slot streams wait for `cuda_stream`; 1: `cuda_stream` waits for the slots."""
+        check(self.lib.wb_stream_fence(self._ctx, int(cuda_stream), direction))
+
     # --------------------------------------------------------------- stage level
     def preprocess(self, frames):
         n = len(frames)
