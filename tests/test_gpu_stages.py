@@ -65,9 +65,11 @@ def test_backbone_batch_invariance(engine, shapes_oracle):
     rng = np.random.default_rng(5)
     pres = np.stack([shapes_oracle.preprocess(rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)) for _ in range(5)])
     e_all, l_all, _ = engine.backbone(pres)
-    for i in (0, 3, 4):
+    e_rev, l_rev, _ = engine.backbone(pres[::-1].copy())            # same batch size, other order: bit-identical
+    assert np.array_equal(e_rev[::-1], e_all) and np.array_equal(l_rev[::-1], l_all)
+    for i in (0, 3, 4):                                             # other batch size: fp32 rounding only
         e1, l1, _ = engine.backbone(pres[i:i + 1])
-        assert np.array_equal(e1[0], e_all[i]) and np.array_equal(l1[0], l_all[i])
+        assert np.abs(e1[0] - e_all[i]).max() < 2e-5 and np.abs(l1[0] - l_all[i]).max() < 1e-4
 
 
 # ------------------------------------------------------------------------------- K7..K9

@@ -95,10 +95,22 @@ void launch_dw(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const
                const float* offset, T* out);
 template <typename T>
 void launch_add(const LaunchCtx& lc, size_t elems, const T* a, const T* b, T* out);
+struct SplitKReduceArgs {
+  const float* partial;  // [splits][M][ld] raw accumulators
+  const float* scale;
+  const float* offset;
+  void* out;  // fp32 or bf16 [M][N]
+  int out_is_bf16;
+  float* enc;
+  float* logits;
+  int M, N, ld, splits, act;
+  int is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1, hw;
+};
+void launch_splitk_reduce(const LaunchCtx& lc, const SplitKReduceArgs& r);
 template <typename T>
 void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w,
                     const float* scale, const float* offset, T* out, float* enc, float* logits,
-                    int num_anchors, int num_classes_p1);
+                    int num_anchors, int num_classes_p1, float* partial, size_t partial_floats);
 void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* enc, const float* logits,
                  const float* anchors, const FrameDesc* frames, const CameraCfg* cams, uint32_t flags,
                  float* dec_boxes, int* cand_count, unsigned long long* cand, int* sel_count,

@@ -5,6 +5,8 @@
 // frozen graph run by watsor/detection/tensorflow_cpu.py:114.  All tensors are NHWC, TF `SAME`
 // padding (asymmetric).  The 1x1 / KxK dense convolutions are one tiled SGEMM with an optional
 // im2col row gather; the bf16 tcgen05 path lives in kernels_tc.cu.
+#include <algorithm>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -99,6 +101,8 @@ struct GemmArgs {
   int in_h, in_w, in_c, out_h, out_w, kh, kw, stride, pad_t, pad_l;
   int act;
   int is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1;
+  int splits;      // split-K: blockIdx.z handles k-tiles [z*kt_per, ...) and writes raw partial sums
+  float* partial;  // [splits][M][ldw]
 };
 
 template <typename T, int BM, int BN, int TM, int TN>
@@ -191,11 +195,14 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  const int KT = g.K / BK;
-  load_tile(0);
-  store_tile(0);
+  const int KT_all = g.K / BK;
+  const int kt_per = (KT_all + g.splits - 1) / g.splits;
+  const int kt0 = blockIdx.z * kt_per;
+  const int KT = min(KT_all, kt0 + kt_per);
+  load_tile(kt0);
+  store_tile(kt0 & 1);
   __syncthreads();
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int kt = kt0; kt < KT; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < KT) load_tile(kt + 1);
 #pragma unroll
@@ -240,6 +247,11 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
       for (int c = 0; c < CG; ++c) {
         const int n = n0 + c * (TX * 4) + tx * 4;
         if (n >= g.N) continue;
+        if (g.splits > 1) {
+          *reinterpret_cast<float4*>(g.partial + ((size_t)blockIdx.z * g.M + m) * g.ldw + n) =
+              make_float4(acc[i][c * 4 + 0], acc[i][c * 4 + 1], acc[i][c * 4 + 2], acc[i][c * 4 + 3]);
+          continue;
+        }
         float v[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
 template <typename T>
 void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w,
                     const float* scale, const float* offset, T* out, float* enc, float* logits,
-                    int num_anchors, int num_classes_p1) {
+                    int num_anchors, int num_classes_p1, float* partial, size_t partial_floats) {
   GemmArgs<T> g;
   g.in = in;
   g.w = w;
@@ -301,18 +313,108 @@ void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, 
   g.n_box = L.n_box;
   g.num_anchors = num_anchors;
   g.ncp1 = num_classes_p1;
+  g.splits = 1;
+  g.partial = partial;
   // big tiles when they still fill the 148 SMs, small tiles otherwise
   long big = (long)((g.M + 127) / 128) * ((g.N + 127) / 128);
   if (big >= 148 && g.N >= 128) {
     dim3 grid((g.N + 127) / 128, (g.M + 127) / 128);
     k_gemm_cc<T, 128, 128, 8, 8><<<grid, 256, 0, lc.stream>>>(g);
-  } else {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-    k_gemm_cc<T, 64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g);
+    ++*lc.launch_counter;
+    return;
   }
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  // latency-bound shapes (few tiles, long K): split K over blockIdx.z so that ~2 waves of CTAs exist;
+  // partial sums go to scratch and are reduced in a fixed order (deterministic) with the epilogue fused
+  const int kt_all = g.K / 16;
+  const long tiles = (long)grid.x * grid.y;
+  if (partial != nullptr && tiles < 120 && kt_all >= 16) {
+    int want = (int)((296 + tiles - 1) / tiles);
+    int splits = std::min(want, kt_all / 8);
+    while (splits > 1 && (size_t)splits * g.M * g.ldw > partial_floats) --splits;
+    if (splits > 1) {
+      const int kt_per = (kt_all + splits - 1) / splits;
+      splits = (kt_all + kt_per - 1) / kt_per;  // no empty split
+      g.splits = splits;
+      grid.z = splits;
+    }
+  }
+  k_gemm_cc<T, 64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g);
+  ++*lc.launch_counter;
+  if (g.splits > 1) {
+    SplitKReduceArgs r;
+    r.partial = partial;
+    r.scale = scale;
+    r.offset = offset;
+    r.out = out;
+    r.out_is_bf16 = sizeof(T) == 2;
+    r.enc = enc;
+    r.logits = logits;
+    r.M = g.M;
+    r.N = g.N;
+    r.ld = g.ldw;
+    r.splits = g.splits;
+    r.act = g.act;
+    r.is_head = g.is_head;
+    r.anchors_per_loc = g.anchors_per_loc;
+    r.row_off = g.row_off;
+    r.n_box = g.n_box;
+    r.num_anchors = g.num_anchors;
+    r.ncp1 = g.ncp1;
+    r.hw = g.out_h * g.out_w;
+    launch_splitk_reduce(lc, r);
+  }
+}
+
+// sums the split-K partial tiles in split order and applies the layer epilogue (affine, ReLU6, store
+// or head scatter).  One thread per 4 output columns.
+__global__ void __launch_bounds__(256) k_splitk_reduce(SplitKReduceArgs r) {
+  const int n4 = r.ld >> 2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)r.M * n4) return;
+  const int m = (int)(idx / n4), n = (int)(idx % n4) * 4;
+  if (n >= r.N) return;
+  float4 acc = *reinterpret_cast<const float4*>(r.partial + (size_t)m * r.ld + n);
+  for (int z = 1; z < r.splits; ++z) {
+    float4 p = *reinterpret_cast<const float4*>(r.partial + ((size_t)z * r.M + m) * r.ld + n);
+    acc.x = __fadd_rn(acc.x, p.x);
+    acc.y = __fadd_rn(acc.y, p.y);
+    acc.z = __fadd_rn(acc.z, p.z);
+    acc.w = __fadd_rn(acc.w, p.w);
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = affine_rn(v[j], __ldg(r.scale + n + j), __ldg(r.offset + n + j));
+    v[j] = r.act == WB_ACT_RELU6 ? relu6f(x) : x;
+  }
+  if (r.is_head) {
+    const int f = m / r.hw, p = m - f * r.hw;
+    const size_t row = (size_t)f * r.num_anchors + r.row_off + (size_t)p * r.anchors_per_loc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n + j;
+      if (nn >= r.N) break;
+      if (nn < r.n_box)
+        r.enc[row * 4 + nn] = v[j];
+      else
+        r.logits[row * r.ncp1 + (nn - r.n_box)] = v[j];
+    }
+  } else if (r.out_is_bf16) {
+    ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(r.out) + (size_t)m * r.N + n, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(r.out) + (size_t)m * r.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+void launch_splitk_reduce(const LaunchCtx& lc, const SplitKReduceArgs& r) {
+  size_t total = (size_t)r.M * (r.ld >> 2);
+  k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(r);
   ++*lc.launch_counter;
 }
+
 template void launch_gemm_cc<float>(const LaunchCtx&, int, const wb_layer&, const float*, const float*, const float*,
-                                    const float*, float*, float*, float*, int, int);
+                                    const float*, float*, float*, float*, int, int, float*, size_t);
 template void launch_gemm_cc<__nv_bfloat16>(const LaunchCtx&, int, const wb_layer&, const __nv_bfloat16*, const float*,
-                                            const float*, const float*, __nv_bfloat16*, float*, float*, int, int);
+                                            const float*, const float*, __nv_bfloat16*, float*, float*, int, int, float*,
+                                            size_t);

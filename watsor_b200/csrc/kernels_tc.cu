@@ -129,6 +129,8 @@ struct TcArgs {
   float* logits;
   int M, N, n_pad, K;  // K in elements
   int block_n, stages, k_blocks;
+  int splits, kb_per;  // split-K over blockIdx.z (partials reduced by k_splitk_reduce)
+  float* partial;      // [splits][M][n_pad]
   int n_main;  // TF32X3: the hi*hi products rotate over n_main TMEM accumulators (+1 for the corrections)
   int act, is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1, hw;
 };
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * g.block_n;
+  const int kb0 = blockIdx.z * g.kb_per;
+  const int nkb = min(g.k_blocks, kb0 + g.kb_per) - kb0;  // k-blocks of this split (>= 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
   const int n_acc = X3 ? g.n_main + 1 : 1;
   uint32_t tmem_cols = 32;
@@ -178,9 +182,10 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < g.k_blocks; ++kb) {
-        const int s = kb % g.stages;
-        const uint32_t ph = (kb / g.stages) & 1;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + it;
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(smem_u32(&empty[s]), ph ^ 1);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t bar = smem_u32(&full[s]);
@@ -194,9 +199,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(TF32, BLOCK_M, g.block_n);
-    for (int kb = 0; kb < g.k_blocks; ++kb) {
-      const int s = kb % g.stages;
-      const uint32_t ph = (kb / g.stages) & 1;
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % g.stages;
+      const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
       tc_fence_after();
       if (lane == 0) {
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
 #pragma unroll
         for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
           const uint32_t koff = k * UMMA_K_BYTES;
-          const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+          const int step = it * (ROW_BYTES / UMMA_K_BYTES) + k;
           if (!X3) {
             umma<TF32>(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
           } else {
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           }
         }
         umma_commit(smem_u32(&empty[s]));
-        if (kb == g.k_blocks - 1) umma_commit(smem_u32(acc_full));
+        if (it == nkb - 1) umma_commit(smem_u32(acc_full));
       }
       __syncwarp();
     }
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
       if (X3) {
-        const int used = min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES));
+        const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
         for (int a = 1; a <= g.n_main; ++a) {
           if (a < g.n_main && a >= used) continue;  // accumulator never written (very small K)
           uint32_t u[16];
@@ -252,6 +257,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       }
       const int n = n0 + c0;
       if (m >= g.M || n >= g.N) continue;
+      if (g.splits > 1) {
+        float* pp = g.partial + ((size_t)blockIdx.z * g.M + m) * g.n_pad + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(pp + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        continue;
+      }
       float y[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -294,9 +307,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   } else if (X3) {
     // ------------------------------------------------------------------ converters (A -> hi / lo)
     const int t = threadIdx.x - 192;  // 0..127
-    for (int kb = 0; kb < g.k_blocks; ++kb) {
-      const int s = kb % g.stages;
-      const uint32_t ph = (kb / g.stages) & 1;
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % g.stages;
+      const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(smem_u32(&full[s]), ph);
       uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
       uint4* lo = a + A_TILE_BYTES / 16;
@@ -451,7 +464,7 @@ void tc_free_weights(TcWeights* w) {
 
 int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L, const void* in,
                    const float* scale, const float* offset, void* out, float* enc, float* logits, int num_anchors,
-                   int num_classes_p1, std::string* err) {
+                   int num_classes_p1, float* partial, size_t partial_floats, std::string* err) {
   const TcLayerWeights& w = tw.layers[layer_index];
   if (!w.ready) {
     *err = "no tensor-core weights for this layer";
@@ -470,6 +483,8 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.n_pad = L.n_pad;
   g.K = L.in_c;
   g.block_n = w.block_n;
+  // wide layers with few row tiles: halve the N tile so that more CTAs (and SMs) take part
+  if (g.n_pad > 128 && g.n_pad % 64 == 0 && (long)((g.M + BLOCK_M - 1) / BLOCK_M) * (g.n_pad / 128) < 120) g.block_n = 64;
   g.k_blocks = (g.K * elem + ROW_BYTES - 1) / ROW_BYTES;
   g.act = L.act;
   g.is_head = L.op == WB_OP_HEAD;
@@ -483,18 +498,42 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.n_main = 1;
   if (mode == TC_TF32X3) g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
   const int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
+  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
+  // latency-bound shapes: split K so that about one wave of CTAs exists (deterministic two-pass reduce)
+  g.splits = 1;
+  g.kb_per = g.k_blocks;
+  g.partial = partial;
+  const long tiles = (long)grid.x * grid.y;
+  if (partial != nullptr && tiles < 74 && g.k_blocks >= 4) {
+    int want = (int)((148 + tiles - 1) / tiles);
+    int splits = std::min(want, g.k_blocks / 2);
+    while (splits > 1 && (size_t)splits * g.M * g.n_pad > partial_floats) --splits;
+    if (splits > 1) {
+      g.kb_per = (g.k_blocks + splits - 1) / splits;
+      g.splits = (g.k_blocks + g.kb_per - 1) / g.kb_per;
+      grid.z = g.splits;
+    }
+  }
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
-  if (stages > g.k_blocks) stages = g.k_blocks;
+  if (stages > g.kb_per) stages = g.kb_per;
   if (stages < 1) stages = 1;
   g.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 8 * (3 * stages + 1) + 16;
   CUtensorMap map_a;
   if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) return 1;
   CUtensorMap map_b, map_b_lo;
-  memcpy(&map_b, w.tmap_b, sizeof(map_b));
-  memcpy(&map_b_lo, w.tmap_b_lo, sizeof(map_b_lo));
-  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
+  if (g.block_n == w.block_n) {
+    memcpy(&map_b, w.tmap_b, sizeof(map_b));
+    memcpy(&map_b_lo, w.tmap_b_lo, sizeof(map_b_lo));
+  } else {
+    if (!make_map(&map_b, w.w, elem, w.n_pad, w.k, g.block_n, err)) return 1;
+    if (mode == TC_TF32X3) {
+      if (!make_map(&map_b_lo, w.w_lo, elem, w.n_pad, w.k, g.block_n, err)) return 1;
+    } else {
+      map_b_lo = map_b;
+    }
+  }
   static bool attr_done[3] = {false, false, false};
   cudaError_t e = cudaSuccess;
   if (mode == TC_BF16) {
@@ -521,5 +560,28 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     return 1;
   }
   ++*lc.launch_counter;
+  if (g.splits > 1) {
+    SplitKReduceArgs r;
+    r.partial = partial;
+    r.scale = scale;
+    r.offset = offset;
+    r.out = out;
+    r.out_is_bf16 = mode == TC_BF16;
+    r.enc = enc;
+    r.logits = logits;
+    r.M = g.M;
+    r.N = g.N;
+    r.ld = g.n_pad;
+    r.splits = g.splits;
+    r.act = g.act;
+    r.is_head = g.is_head;
+    r.anchors_per_loc = g.anchors_per_loc;
+    r.row_off = g.row_off;
+    r.n_box = g.n_box;
+    r.num_anchors = g.num_anchors;
+    r.ncp1 = g.ncp1;
+    r.hw = g.hw;
+    launch_splitk_reduce(lc, r);
+  }
   return 0;
 }

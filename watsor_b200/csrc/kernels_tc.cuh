@@ -27,4 +27,4 @@ int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb
 void tc_free_weights(TcWeights* w);
 int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L, const void* in,
                    const float* scale, const float* offset, void* out, float* enc, float* logits, int num_anchors,
-                   int num_classes_p1, std::string* err);
+                   int num_classes_p1, float* partial, size_t partial_floats, std::string* err);

@@ -40,6 +40,8 @@ struct Slot {
   void* arena = nullptr;
   float* d_pre = nullptr;
   float *d_enc = nullptr, *d_logits = nullptr, *d_dec = nullptr;
+  float* d_partial = nullptr;  // split-K scratch
+  size_t partial_floats = 0;
   int *d_cand_count = nullptr, *d_sel_count = nullptr;
   unsigned long long *d_cand = nullptr, *d_sel = nullptr;
   wb_detection *d_out = nullptr, *h_out = nullptr;
@@ -111,6 +113,8 @@ static int alloc_slot(wb_ctx* c, Slot& s) {
   CK(cudaMalloc(&s.d_enc, sizeof(float) * (size_t)B * N * 4));
   CK(cudaMalloc(&s.d_logits, sizeof(float) * (size_t)B * N * (C + 1)));
   CK(cudaMalloc(&s.d_dec, sizeof(float) * (size_t)B * N * 4));
+  s.partial_floats = (size_t)4 * 1024 * 1024 + (size_t)B * 512 * 1024;
+  CK(cudaMalloc(&s.d_partial, sizeof(float) * s.partial_floats));
   CK(cudaMalloc(&s.d_cand_count, sizeof(int) * (size_t)B * C));
   CK(cudaMalloc(&s.d_sel_count, sizeof(int) * (size_t)B * C));
   CK(cudaMalloc(&s.d_cand, sizeof(unsigned long long) * (size_t)B * C * N));
@@ -214,6 +218,7 @@ int wb_destroy(wb_ctx* c) {
     cudaFree(s.d_enc);
     cudaFree(s.d_logits);
     cudaFree(s.d_dec);
+    cudaFree(s.d_partial);
     cudaFree(s.d_cand_count);
     cudaFree(s.d_sel_count);
     cudaFree(s.d_cand);
@@ -385,10 +390,10 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
         if (c->precision != 0 && tc_layer_supported(L)) {
           std::string err;
           if (tc_launch_gemm(lc, c->tc, (int)li, n, L, static_cast<const void*>(in), sc, of, static_cast<void*>(outp),
-                             s.d_enc, s.d_logits, NA, C1, &err))
+                             s.d_enc, s.d_logits, NA, C1, s.d_partial, s.partial_floats, &err))
             return fail("layer " + std::string(L.name) + ": " + err);
         } else {
-          launch_gemm_cc<T>(lc, n, L, in, w, sc, of, outp, s.d_enc, s.d_logits, NA, C1);
+          launch_gemm_cc<T>(lc, n, L, in, w, sc, of, outp, s.d_enc, s.d_logits, NA, C1, s.d_partial, s.partial_floats);
         }
         break;
       default:
