@@ -117,3 +117,43 @@ def test_mask_filter_random_masks(seed):
     for r in range(200):
         want = oracle(dets[r])
         assert f(rows[r]) == want and list(rows[r].zones) == dets[r].zones, (r, dets[r].key())
+
+
+def test_track_filter_known_answers():      # test_filter.py:76-96
+    from watsor_b200.filter.track import TrackFilter
+    t = TrackFilter(sensitivity=1, history=2)
+    dets, sus = t([Detection(label=1, confidence=0.70, bounding_box=BoundingBox(50, 50, 60, 60)),
+                   Detection(label=1, confidence=0.70, bounding_box=BoundingBox(10, 10, 30, 30))])
+    box = lambda d: [d.bounding_box.x_min, d.bounding_box.y_min, d.bounding_box.x_max, d.bounding_box.y_max]
+    assert sus and [box(d) for d in dets] == [[50, 50, 60, 60], [10, 10, 30, 30]]
+    dets, sus = t([Detection(label=1, confidence=0.70, bounding_box=BoundingBox(40, 40, 55, 55)),
+                   Detection(label=1, confidence=0.70, bounding_box=BoundingBox(80, 80, 90, 90))])
+    assert sus and [box(d) for d in dets] == [[40, 40, 60, 60], [80, 80, 90, 90]]
+
+
+def test_track_filter_fused_predicates_and_sieve_match_oracle():
+    """TrackFilter([Confidence, Area, Mask]) + sieve write-back vs the oracle's restatement of
+    track.py / sieve.py on random rows over several frames (history and sensitivity exercised)."""
+    from oracle.filters import TrackOracle
+    from watsor_b200.filter.sieve import sieve_frame
+    from watsor_b200.filter.track import TrackFilter
+    ours = TrackFilter([ConfidenceFilter(PORCH_CONFIG), AreaFilter(PORCH_CONFIG), MaskFilter(PORCH_CONFIG)],
+                       sensitivity=2, history=3)
+    oracle = TrackOracle([ConfidenceOracle(PORCH_CONFIG), AreaOracle(PORCH_CONFIG), MaskOracle(PORCH_CONFIG)],
+                         sensitivity=2, history=3)
+    rng = np.random.default_rng(7)
+    anchors = [(int(rng.integers(0, 500)), int(rng.integers(0, 380)), int(rng.integers(1, 4))) for _ in range(6)]
+    for frame in range(8):
+        rows, dets = random_rows(rng, 640, 480, 100)
+        for i, (x, y, lab) in enumerate(anchors):                     # persistent objects that jitter a little
+            dx, dy = int(rng.integers(-3, 4)), int(rng.integers(-3, 4))
+            rows[i].label, rows[i].confidence = lab, 0.9
+            rows[i].bounding_box = BoundingBox(x + dx, y + dy, x + 120 + dx, y + 90 + dy)
+            dets[i] = Det(lab, 0.9, (x + dx, y + dy, x + 120 + dx, y + 90 + dy))
+        sus = sieve_frame(rows, [ours])
+        want, want_sus = oracle(dets)
+        assert sus == want_sus
+        got = [(rows[r].label, rows[r].confidence, rows[r].bounding_box.x_min, rows[r].bounding_box.y_min,
+                rows[r].bounding_box.x_max, rows[r].bounding_box.y_max, list(rows[r].zones)) for r in range(100)]
+        exp = [(d.label, d.confidence, d.x_min, d.y_min, d.x_max, d.y_max, d.zones) for d in want]
+        assert got[:len(exp)] == exp and all(g == (0, 0.0, 0, 0, 0, 0, [0] * 10) for g in got[len(exp):])
