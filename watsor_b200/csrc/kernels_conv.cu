@@ -52,9 +52,80 @@ __global__ void __launch_bounds__(256)
   ActIO<T>::st4(out + idx * 4, v);
 }
 
+// strip variant: one thread = 4 consecutive output pixels x 4 channels; the (4-1)*S+3 input columns
+// of a row are loaded once and reused by the four outputs (2x fewer loads at stride 1)
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+    k_dw_strip(int n, wb_layer L, const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+               const float* __restrict__ offset, T* __restrict__ out) {
+  constexpr int NC = 3 * S + 3;
+  const int c4n = L.out_c >> 2;
+  const int xs_n = (L.out_w + 3) >> 2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * L.out_h * xs_n * c4n;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4n) * 4;
+  size_t p = idx / c4n;
+  const int ox0 = (int)(p % xs_n) * 4;
+  p /= xs_n;
+  const int oy = (int)(p % L.out_h);
+  const int f = (int)(p / L.out_h);
+  float4 wr[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wr[t] = __ldg(reinterpret_cast<const float4*>(w + t * L.out_c + c));
+  float4 acc[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const T* base = in + (size_t)f * L.in_h * L.in_w * L.in_c + c;
+  const int iy0 = oy * S - (int)L.pad_t, ix0 = ox0 * S - (int)L.pad_l;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = iy0 + ky;
+    if (iy < 0 || iy >= (int)L.in_h) continue;
+    float4 col[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int ix = ix0 + j;
+      col[j] = (ix >= 0 && ix < (int)L.in_w) ? ActIO<T>::ld4(base + ((size_t)iy * L.in_w + ix) * L.in_c)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 x = col[o * S + kx], ww = wr[ky * 3 + kx];
+        acc[o].x = fmaf(x.x, ww.x, acc[o].x);
+        acc[o].y = fmaf(x.y, ww.y, acc[o].y);
+        acc[o].z = fmaf(x.z, ww.z, acc[o].z);
+        acc[o].w = fmaf(x.w, ww.w, acc[o].w);
+      }
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+  const float4 of = __ldg(reinterpret_cast<const float4*>(offset + c));
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int ox = ox0 + o;
+    if (ox >= (int)L.out_w) break;
+    float4 v = make_float4(affine_rn(acc[o].x, sc.x, of.x), affine_rn(acc[o].y, sc.y, of.y),
+                           affine_rn(acc[o].z, sc.z, of.z), affine_rn(acc[o].w, sc.w, of.w));
+    if (L.act == WB_ACT_RELU6) v = make_float4(relu6f(v.x), relu6f(v.y), relu6f(v.z), relu6f(v.w));
+    ActIO<T>::st4(out + (((size_t)f * L.out_h + oy) * L.out_w + ox) * L.out_c + c, v);
+  }
+}
+
 template <typename T>
 void launch_dw(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w, const float* scale,
                const float* offset, T* out) {
+  if ((L.stride == 1 || L.stride == 2) && L.out_w >= 4) {
+    size_t total = (size_t)n * L.out_h * ((L.out_w + 3) >> 2) * (L.out_c >> 2);
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (L.stride == 1)
+      k_dw_strip<T, 1><<<blocks, 256, 0, lc.stream>>>(n, L, in, w, scale, offset, out);
+    else
+      k_dw_strip<T, 2><<<blocks, 256, 0, lc.stream>>>(n, L, in, w, scale, offset, out);
+    ++*lc.launch_counter;
+    return;
+  }
   size_t total = (size_t)n * L.out_h * L.out_w * (L.out_c >> 2);
   k_dw<T><<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(n, L, in, w, scale, offset, out);
   ++*lc.launch_counter;

@@ -483,8 +483,6 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.n_pad = L.n_pad;
   g.K = L.in_c;
   g.block_n = w.block_n;
-  // wide layers with few row tiles: halve the N tile so that more CTAs (and SMs) take part
-  if (g.n_pad > 128 && g.n_pad % 64 == 0 && (long)((g.M + BLOCK_M - 1) / BLOCK_M) * (g.n_pad / 128) < 120) g.block_n = 64;
   g.k_blocks = (g.K * elem + ROW_BYTES - 1) / ROW_BYTES;
   g.act = L.act;
   g.is_head = L.op == WB_OP_HEAD;

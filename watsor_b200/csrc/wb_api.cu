@@ -11,7 +11,7 @@
 #include "kernels_tc.cuh"
 
 #define WB_MAX_CAMERAS 256
-#define WB_SLOTS 3
+#define WB_SLOTS 6
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) {
