@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a_ok[i]) {
         if (!im2col) {
-          v = ActIO<T>::ld4(g.in + (size_t)(m0 + a_row[i]) * g.K + k0 + a_kq[i] * 4);
+          if (k0 + a_kq[i] * 4 < g.K) v = ActIO<T>::ld4(g.in + (size_t)(m0 + a_row[i]) * g.K + k0 + a_kq[i] * 4);
         } else {
           int tap = k0 / g.in_c, ci = k0 - tap * g.in_c;
           int ky = tap / g.kw, kx = tap - ky * g.kw;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
     for (int i = 0; i < B_F4; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       int n = n0 + b_n[i];
-      if (n < g.ldw) v = __ldg(reinterpret_cast<const float4*>(g.w + (size_t)(k0 + b_k[i]) * g.ldw + n));
+      if (n < g.ldw && k0 + b_k[i] < g.K) v = __ldg(reinterpret_cast<const float4*>(g.w + (size_t)(k0 + b_k[i]) * g.ldw + n));
       b_reg[i] = v;
     }
   };
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_gemm_cc(GemmArgs<T> g) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  const int KT_all = g.K / BK;
+  const int KT_all = (g.K + BK - 1) / BK;
   const int kt_per = (KT_all + g.splits - 1) / g.splits;
   const int kt0 = blockIdx.z * kt_per;
   const int KT = min(KT_all, kt0 + kt_per);
@@ -397,7 +397,7 @@ void launch_gemm_cc(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, 
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
   // latency-bound shapes (few tiles, long K): split K over blockIdx.z so that ~2 waves of CTAs exist;
   // partial sums go to scratch and are reduced in a fixed order (deterministic) with the epilogue fused
-  const int kt_all = g.K / 16;
+  const int kt_all = (g.K + 15) / 16;
   const long tiles = (long)grid.x * grid.y;
   if (partial != nullptr && tiles < 120 && kt_all >= 16) {
     int want = (int)((296 + tiles - 1) / tiles);

@@ -381,19 +381,16 @@ bool make_map(CUtensorMap* map, const void* base, int elem_bytes, int rows, int 
 }
 
 int pick_block_n(int n_pad) {
-  if (n_pad <= 128) return n_pad;            // multiples of 16 up to 128: one N tile
-  if (n_pad % 128 == 0) return 128;
-  if (n_pad % 96 == 0) return 96;
-  if (n_pad % 64 == 0) return 64;
-  if (n_pad % 48 == 0) return 48;
-  if (n_pad % 32 == 0) return 32;
+  if (n_pad <= 128) return n_pad;  // multiples of 16 up to 128: one N tile
+  for (int bn = 128; bn >= 16; bn -= 16)
+    if (n_pad % bn == 0) return bn;  // largest UMMA width (multiple of 16) that tiles N exactly
   return 16;
 }
 
 }  // namespace
 
 bool tc_layer_supported(const wb_layer& L) {
-  return (L.op == WB_OP_PW || L.op == WB_OP_HEAD) && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.in_c % 16 == 0;
+  return (L.op == WB_OP_PW || L.op == WB_OP_HEAD) && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.in_c % 4 == 0;
 }
 
 int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb_tensor_entry>& tensors,

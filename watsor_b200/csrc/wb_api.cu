@@ -168,8 +168,10 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   REQUIRE(c->hdr.score_thr >= 0.f, "negative score threshold is not supported");
   REQUIRE(c->hdr.num_anchors >= 1 && c->hdr.num_anchors <= 16384, "num_anchors out of range");
   for (auto& L : c->layers) {
-    if (L.op == WB_OP_PW || L.op == WB_OP_CONV || L.op == WB_OP_HEAD)
-      REQUIRE(L.in_c % 16 == 0, std::string("layer ") + L.name + ": in_c must be a multiple of 16");
+    if (L.op == WB_OP_PW || L.op == WB_OP_HEAD)
+      REQUIRE(L.in_c % 4 == 0, std::string("layer ") + L.name + ": in_c must be a multiple of 4");
+    if (L.op == WB_OP_CONV)
+      REQUIRE(L.in_c % 16 == 0, std::string("layer ") + L.name + ": KxK convs need in_c to be a multiple of 16");
     if (L.op == WB_OP_DW) REQUIRE(L.out_c % 4 == 0 && L.kh == 3 && L.kw == 3, "depthwise must be 3x3, C%4==0");
     if (L.op == WB_OP_PW || L.op == WB_OP_CONV) REQUIRE(L.out_c % 4 == 0, "out_c must be a multiple of 4");
   }

@@ -555,3 +555,92 @@ def synthetic_ssd_mobilenet_v1(num_classes=90, seed=0, score_thr=1e-8, input_siz
     m.anchors_tensor = m.add_tensor(ssd_anchors(fmaps))
     m.plan_arena()
     return m
+
+
+def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_size=300):
+    """SSD-MobileNet-v2 architecture descriptor (TF-slim mobilenet_v2, depth multiplier 1.0, plus the
+    SSD feature-map layout of ssd_mobilenet_v2_feature_extractor: taps `layer_15/expansion_output`
+    19x19x576 and `layer_19` 10x10x1280, then four 1x1 -> 3x3/s2 extra pairs 512/256/256/128) with
+    seeded synthetic weights.  BASELINE.json's 640x480 configs name this model; no weights for it
+    exist offline, so it runs on He-initialised tensors and is checked GPU-vs-oracle only.
+
+    Inverted residual block: 1x1 expand (x6, BN, ReLU6) -> 3x3 depthwise (stride s, BN, ReLU6) ->
+    1x1 linear projection (BN), residual add when stride == 1 and channels match.
+    """
+    rng = np.random.default_rng(seed)
+    m = Model(name='ssd_mobilenet_v2_synthetic_c%d' % num_classes, input_h=input_size, input_w=input_size,
+              num_classes=num_classes, score_thr=score_thr, iou_thr=0.6,
+              pre_mul=float(np.float32(2.0 / 255.0)), pre_sub=1.0)
+    em = _Emitter(m)
+    em.shape['image'] = (input_size, input_size, 3)
+
+    def he(shape, fan_in, gain=2.0):
+        return (rng.standard_normal(shape) * np.sqrt(gain / fan_in)).astype(np.float32)
+
+    def bn(c, spread=0.1):
+        return ((1.0 + spread * rng.standard_normal(c)).astype(np.float32),
+                (spread * rng.standard_normal(c)).astype(np.float32))
+
+    s, o = bn(32)
+    em.conv('Conv', 'image', 'conv0', he((3, 3, 3, 32), 27), s, o, 2, ACT_RELU6)
+    cur, c_in = 'conv0', 32
+    # expanded_conv (t = 1): depthwise + linear projection to 16
+    s, o = bn(32)
+    em.conv('expanded_conv/depthwise', cur, 'b0dw', he((3, 3, 32, 1), 9) * 1.5, s, o, 1, ACT_RELU6, depthwise=True)
+    s, o = bn(16)
+    em.conv('expanded_conv/project', 'b0dw', 'b0', he((1, 1, 32, 16), 32, 1.0), s, o, 1, ACT_NONE)
+    cur, c_in = 'b0', 16
+    tap15 = None
+    idx = 1
+    for (t, c, n, stride0) in [(6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]:
+        for i in range(n):
+            stride = stride0 if i == 0 else 1
+            name = 'expanded_conv_%d' % idx
+            ce = c_in * t
+            s, o = bn(ce)
+            em.conv(name + '/expand', cur, name + 'e', he((1, 1, c_in, ce), c_in), s, o, 1, ACT_RELU6)
+            if idx == 13:
+                tap15 = name + 'e'                     # layer_15/expansion_output
+            s, o = bn(ce)
+            em.conv(name + '/depthwise', name + 'e', name + 'd', he((3, 3, ce, 1), 9) * 1.5, s, o, stride,
+                    ACT_RELU6, depthwise=True)
+            s, o = bn(c)
+            em.conv(name + '/project', name + 'd', name + 'p', he((1, 1, ce, c), ce, 1.0), s, o, 1, ACT_NONE)
+            if stride == 1 and c_in == c:
+                em.add(name + '/add', cur, name + 'p', name + 'a')
+                cur = name + 'a'
+            else:
+                cur = name + 'p'
+            c_in = c
+            idx += 1
+    s, o = bn(1280)
+    em.conv('Conv_1', cur, 'conv1', he((1, 1, c_in, 1280), c_in), s, o, 1, ACT_RELU6)
+    cur, c_in = 'conv1', 1280
+    feats = [tap15, 'conv1']
+    for j, (mid, out_c) in enumerate([(256, 512), (128, 256), (128, 256), (64, 128)], 2):
+        s, o = bn(mid)
+        em.conv('layer_19_1_Conv2d_%d_1x1_%d' % (j, mid), cur, 'x%da' % j, he((1, 1, c_in, mid), c_in), s, o, 1, ACT_RELU6)
+        s, o = bn(out_c)
+        em.conv('layer_19_2_Conv2d_%d_3x3_s2_%d' % (j, out_c), 'x%da' % j, 'x%db' % j, he((3, 3, mid, out_c), 9 * mid),
+                s, o, 2, ACT_RELU6)
+        cur, c_in = 'x%db' % j, out_c
+        feats.append(cur)
+    row, fmaps, head_layers = 0, [], []
+    for k, f in enumerate(feats):
+        h, w_, c = em.shape[f]
+        a = 3 if k == 0 else 6
+        fmaps.append((h, w_))
+        n0 = len(m.layers)
+        row += em.head('BoxPredictor_%d' % k, f, he((1, 1, c, a * 4), c) * 0.5,
+                       (0.05 * rng.standard_normal(a * 4)).astype(np.float32),
+                       he((1, 1, c, a * (num_classes + 1)), c),
+                       (-2.0 + 0.5 * rng.standard_normal(a * (num_classes + 1))).astype(np.float32),
+                       row, num_classes + 1)
+        head_layers.append(m.layers.pop(n0))
+    for hl in head_layers:
+        at = max(i for i, l in enumerate(m.layers) if l.dst == hl.src)
+        m.layers.insert(at + 1, hl)
+    m.num_anchors = row
+    m.anchors_tensor = m.add_tensor(ssd_anchors(fmaps))
+    m.plan_arena()
+    return m
