@@ -28,7 +28,10 @@ def tiny_model(K, N, hw, seed=0):
 # (K, N, hw, batch): K = 32 is a half-filled swizzle row in bf16, N = 48 / 96 are non-power-of-two
 # UMMA widths, M = 9 is a mostly out-of-bounds TMA box, 1024x1024 runs the full smem pipeline
 CASES = [(512, 512, 19, 4), (32, 64, 32, 2), (1024, 1024, 10, 8), (256, 48, 3, 1), (64, 128, 20, 3),
-         (128, 96, 7, 2), (16, 16, 5, 1)]
+         (128, 96, 7, 2), (16, 16, 5, 1),
+         # >= 148 output tiles: the persistent kernel (double-buffered TMEM, TMA-store epilogue); the last
+         # row tile is partial in each (M = 22500, 28125, 19200+) and 256 columns make two N tiles
+         (32, 64, 150, 1), (64, 128, 75, 5), (128, 256, 41, 12), (24, 128, 150, 2)]
 
 
 @pytest.mark.parametrize('precision,rel_tol', [(2, 3e-6), (3, 4e-3), (1, 1.5e-2)],

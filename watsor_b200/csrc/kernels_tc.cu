@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels_tc.cuh"
@@ -341,6 +342,241 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant for layers with many output tiles (the 150x150 / 75x75 / 38x38 maps): one CTA per
+// SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem stage ring runs continuously
+// across tiles, the TMEM accumulators are double-buffered (the epilogue of tile j overlaps the TMA /
+// convert / MMA work of tile j+1) and the epilogue leaves through 128B-swizzled staging buffers and
+// TMA stores (cp.async.bulk.tensor ... global.shared::cta), i.e. fully coalesced 128-byte rows.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
+    k_gemm_tc_persist(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
+                      TcArgs g) {
+  constexpr bool TF32 = MODE != 0;
+  constexpr bool X3 = MODE == 2;
+  constexpr int ELEM = TF32 ? 4 : 2;
+  constexpr int K_PER_BLOCK = ROW_BYTES / ELEM;
+  constexpr int CW = TF32 ? 32 : 64;  // output columns per 128-byte staging row
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = g.block_n * ROW_BYTES;
+  const int stage_bytes = A_TILE_BYTES * (X3 ? 2 : 1) + b_tile_bytes * (X3 ? 2 : 1);
+  uint8_t* staging = smem + (size_t)g.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  uint64_t* empty = full + g.stages;
+  uint64_t* conv = empty + g.stages;
+  uint64_t* acc_full = conv + g.stages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = g.n_pad / g.block_n;
+  const int num_tiles = ((g.M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+  const int n_acc = X3 ? g.n_main + 1 : 1;
+  const int set_cols = n_acc * g.block_n;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * set_cols) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&conv[s]), 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BLOCK_M, n0 = (t % n_tiles) * g.block_n;
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1;
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          const uint32_t bar = smem_u32(&full[s]);
+          mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
+          tma_load_2d(smem_u32(st), &map_a, bar, kb * K_PER_BLOCK, m0);
+          uint8_t* sb = st + A_TILE_BYTES * (X3 ? 2 : 1);
+          tma_load_2d(smem_u32(sb), &map_b, bar, kb * K_PER_BLOCK, n0);
+          if (X3) tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bar, kb * K_PER_BLOCK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(TF32, BLOCK_M, g.block_n);
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * set_cols);
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
+        mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * (X3 ? 2 : 1)), b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+            const uint32_t koff = k * UMMA_K_BYTES;
+            const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+            if (!X3) {
+              umma<TF32>(acc0, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+            } else {
+              const uint32_t d_main = acc0 + (uint32_t)((step % g.n_main) * g.block_n);
+              const uint32_t d_corr = acc0 + (uint32_t)(g.n_main * g.block_n);
+              umma<TF32>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
+              umma<TF32>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+              umma<TF32>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+            }
+          }
+          umma_commit(smem_u32(&empty[s]));
+          if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    uint8_t* my_stage = staging + (size_t)q * 2 * 4096;
+    const int used = X3 ? min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES)) : 1;
+    int j = 0, chunk_no = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const int m0 = (t / n_tiles) * BLOCK_M, n0 = (t % n_tiles) * g.block_n;
+      mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
+      for (int c0 = 0; c0 < g.block_n; c0 += CW, ++chunk_no) {
+        float y[CW];
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+          uint32_t v[16];
+          tmem_ld16(acc0 + (uint32_t)(c0 + h * 16), v);
+          tmem_ld_wait();
+          if (X3) {
+            for (int a = 1; a <= g.n_main; ++a) {
+              if (a < g.n_main && a >= used) continue;
+              uint32_t u[16];
+              tmem_ld16(acc0 + (uint32_t)(a * g.block_n + c0 + h * 16), u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(u[i])));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int nn = n0 + c0 + h * 16 + i;
+            float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
+            y[h * 16 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+          }
+        }
+        // staging buffer (chunk_no & 1) was last used two chunks ago: its TMA store must have read it
+        if (chunk_no >= 2) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* sb = my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 pk;
+          if (TF32) {
+            pk.x = __float_as_uint(y[c * 4 + 0]);
+            pk.y = __float_as_uint(y[c * 4 + 1]);
+            pk.z = __float_as_uint(y[c * 4 + 2]);
+            pk.w = __float_as_uint(y[c * 4 + 3]);
+          } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[c * 8 + 0], y[c * 8 + 1]), p1 = __floats2bfloat162_rn(y[c * 8 + 2], y[c * 8 + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[c * 8 + 4], y[c * 8 + 5]), p3 = __floats2bfloat162_rn(y[c * 8 + 6], y[c * 8 + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2);
+            pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          }
+          *reinterpret_cast<uint4*>(sb + ((c ^ (lane & 7)) << 4)) = pk;  // 128B swizzle: chunk ^= row % 8
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), n0 + c0, m0 + q * 32);
+          bulk_commit();
+        }
+      }
+      // every TMEM read of this tile has completed: hand the accumulator set back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  } else if (X3) {
+    const int tt = threadIdx.x - 192;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
+        mbar_wait(smem_u32(&full[s]), ph);
+        uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
+        uint4* lo = a + A_TILE_BYTES / 16;
+#pragma unroll 4
+        for (int i = tt; i < A_TILE_BYTES / 16; i += 128) {
+          uint4 x = a[i], h, l;
+          h.x = x.x & 0xFFFFE000u;
+          h.y = x.y & 0xFFFFE000u;
+          h.z = x.z & 0xFFFFE000u;
+          h.w = x.w & 0xFFFFE000u;
+          l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(h.x))) & 0xFFFFE000u;
+          l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
+          l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
+          l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
+          a[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&conv[s]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // -------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -375,6 +611,27 @@ bool make_map(CUtensorMap* map, const void* base, int elem_bytes, int rows, int 
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows " + std::to_string(rows) +
            ", k " + std::to_string(k) + ", box_rows " + std::to_string(box_rows) + ")";
+    return false;
+  }
+  return true;
+}
+
+// output matrix [rows][n] (fp32 or bf16) -> tensor map with a (128 B x 32 rows) box, 128B swizzle
+bool make_out_map(CUtensorMap* map, void* base, int elem_bytes, int rows, int n, std::string* err) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return false;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)n * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem_bytes), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled (output) failed with code " + std::to_string((int)r);
     return false;
   }
   return true;
@@ -491,7 +748,6 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.hw = L.out_h * L.out_w;
   const int x3 = mode == TC_TF32X3 ? 2 : 1;
   g.n_main = 1;
-  if (mode == TC_TF32X3) g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
   const int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
   dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
   // latency-bound shapes: split K so that about one wave of CTAs exists (deterministic two-pass reduce)
@@ -509,12 +765,30 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       grid.z = g.splits;
     }
   }
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > 6) stages = 6;
-  if (stages > g.kb_per) stages = g.kb_per;
+  // many-tile layers: persistent kernel (double-buffered TMEM, TMA-store epilogue)
+  const int cw = mode == TC_BF16 ? 64 : 32;
+  bool persist = !g.is_head && g.splits == 1 && tiles >= 148 && g.N == g.n_pad && g.block_n % cw == 0 &&
+                 g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
+  if (persist && mode == TC_TF32X3) {
+    g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
+    if (2 * (g.n_main + 1) * g.block_n > 512) persist = false;
+  }
+  if (persist && mode != TC_TF32X3 && 2 * g.block_n > 512) persist = false;
+  int stages;
+  if (persist) {
+    stages = (225 * 1024 - STAGING_BYTES) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) persist = false;
+  }
+  if (!persist) {
+    if (mode == TC_TF32X3) g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
+    stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages > g.kb_per) stages = g.kb_per;
+  }
   if (stages < 1) stages = 1;
   g.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 8 * (3 * stages + 1) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16;
   CUtensorMap map_a;
   if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) return 1;
   CUtensorMap map_b, map_b_lo;
@@ -529,9 +803,25 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       map_b_lo = map_b;
     }
   }
-  static bool attr_done[3] = {false, false, false};
+  static bool attr_done[6] = {false, false, false, false, false, false};
   cudaError_t e = cudaSuccess;
-  if (mode == TC_BF16) {
+  if (persist) {
+    CUtensorMap map_out;
+    if (!make_out_map(&map_out, out, elem, g.M, g.N, err)) return 1;
+    const int idx = 3 + (mode == TC_BF16 ? 0 : (mode == TC_TF32X1 ? 1 : 2));
+    dim3 pgrid((unsigned)std::min<long>(tiles, 148));
+    if (mode == TC_BF16) {
+      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      k_gemm_tc_persist<0><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
+    } else if (mode == TC_TF32X1) {
+      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      k_gemm_tc_persist<1><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
+    } else {
+      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      k_gemm_tc_persist<2><<<pgrid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
+    }
+    attr_done[idx] = true;
+  } else if (mode == TC_BF16) {
     if (!attr_done[0]) {
       e = cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       attr_done[0] = true;
