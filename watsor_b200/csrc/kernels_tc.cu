@@ -781,7 +781,12 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     if (stages < 2) persist = false;
   }
   if (!persist) {
-    if (mode == TC_TF32X3) g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
+    if (mode == TC_TF32X3) {
+      g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
+      // short accumulation chains (split-K tails, small K) carry no measurable truncation bias: one main
+      // accumulator halves the TMEM footprint, so two such CTAs can share an SM
+      if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;
+    }
     stages = (200 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages > g.kb_per) stages = g.kb_per;

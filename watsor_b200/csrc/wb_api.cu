@@ -729,19 +729,31 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
   REQUIRE(max_launches >= nl + 1, "max_launches too small");
   std::vector<cudaEvent_t> ev(nl + 2);
   for (auto& e : ev) CK(cudaEventCreate(&e));
+  // every layer is launched REPS times back to back between two events (layers are idempotent: they
+  // never write their own input), so host launch gaps do not leak into the per-kernel time
+  const int REPS = 10;
+  s.launches = 0;
+  if (int rc = run_all(c, s, st, n, 0)) return rc;  // warm-up, also fills every activation buffer
   s.launches = 0;
   CK(cudaEventRecord(ev[0], st));
   for (int li = 0; li < nl; ++li) {
-    int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, li, li)
-                               : run_layers<float>(c, s, st, n, nullptr, li, li);
-    if (rc) return rc;
+    for (int r = 0; r < REPS; ++r) {
+      int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, li, li)
+                                 : run_layers<float>(c, s, st, n, nullptr, li, li);
+      if (rc) return rc;
+    }
     CK(cudaEventRecord(ev[li + 1], st));
     kinds[li] = (int)c->layers[li].op;
   }
-  if (int rc = run_post(c, s, st, n, 0)) return rc;
+  for (int r = 0; r < REPS; ++r)
+    if (int rc = run_post(c, s, st, n, 0)) return rc;
   CK(cudaEventRecord(ev[nl + 1], st));
   CK(cudaEventSynchronize(ev[nl + 1]));
-  for (int li = 0; li <= nl; ++li) CK(cudaEventElapsedTime(&ms[li], ev[li], ev[li + 1]));
+  for (int li = 0; li <= nl; ++li) {
+    CK(cudaEventElapsedTime(&ms[li], ev[li], ev[li + 1]));
+    ms[li] /= REPS;
+  }
+  s.launches /= REPS;
   kinds[nl] = 100;
   for (auto& e : ev) cudaEventDestroy(e);
   *n_out = nl + 1;
