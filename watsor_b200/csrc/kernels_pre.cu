@@ -15,8 +15,10 @@ struct AxisTap {
 
 // TF legacy sampling: scale = in/(float)out; pos = dst*scale; lo = floor(pos);
 // hi = min(ceil(pos), in-1); lerp = pos - floor(pos).
-__device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, int out_size) {
-  float scale = __fdiv_rn((float)in_size, (float)out_size);
+__device__ __forceinline__ float axis_scale(int in_size, int out_size) {
+  return __fdiv_rn((float)in_size, (float)out_size);
+}
+__device__ __forceinline__ AxisTap axis_tap(int dst, int in_size, float scale) {
   float pos = __fmul_rn((float)dst, scale);
   float fl = floorf(pos);
   AxisTap t;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(256) k_preprocess_f32(const FrameDesc* __restr
   if (p >= oh * ow) return;
   FrameDesc fd = frames[blockIdx.y];
   int oy = p / ow, ox = p - oy * ow;
-  AxisTap ty = axis_tap(oy, fd.h, oh), tx = axis_tap(ox, fd.w, ow);
+  AxisTap ty = axis_tap(oy, fd.h, axis_scale(fd.h, oh)), tx = axis_tap(ox, fd.w, axis_scale(fd.w, ow));
   float v[3];
   resized_pixel(fd.ptr, fd.w, ty, tx, mul, sub, v);
   float* o = out + ((size_t)blockIdx.y * oh * ow + p) * 3;
@@ -97,7 +99,12 @@ __global__ void __launch_bounds__(ST_TY* ST_TX)
   // resized tile; rows/cols outside the 300x300 image are the SAME-padding zeros
   const int ry0 = oy0 * S - (int)L.pad_t, rx0 = ox0 * S - (int)L.pad_l;
   FrameDesc fd;
-  if (pre == nullptr) fd = frames[f];
+  float sy = 1.f, sx = 1.f;
+  if (pre == nullptr) {
+    fd = frames[f];
+    sy = axis_scale(fd.h, in_h);  // hoisted: one division per thread, not per sampled pixel
+    sx = axis_scale(fd.w, in_w);
+  }
   for (int i = tid; i < tile_h * tile_w; i += blockDim.x) {
     int ly = i / tile_w, lx = i - ly * tile_w;
     int ry = ry0 + ly, rx = rx0 + lx;
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(ST_TY* ST_TX)
         v[1] = p[1];
         v[2] = p[2];
       } else {
-        AxisTap ty = axis_tap(ry, fd.h, in_h), tx = axis_tap(rx, fd.w, in_w);
+        AxisTap ty = axis_tap(ry, fd.h, sy), tx = axis_tap(rx, fd.w, sx);
         resized_pixel(fd.ptr, fd.w, ty, tx, mul, sub, v);
       }
     }

@@ -93,6 +93,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16 accumulator columns of this thread's row, summed over the TF32X3 partial accumulators in the fixed
+// order ((main0 + main1) + main2) + corr.  All tcgen05.ld are issued before the single wait::ld, so the
+// TMEM round trips overlap instead of serialising.
+template <bool X3>
+__device__ __forceinline__ void load_acc16(uint32_t taddr, int block_n, int n_main, int used, uint32_t* v) {
+  if (!X3) {
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    return;
+  }
+  uint32_t u1[16], u2[16], uc[16];
+  tmem_ld16(taddr, v);
+  if (used > 1) tmem_ld16(taddr + (uint32_t)block_n, u1);
+  if (used > 2) tmem_ld16(taddr + (uint32_t)(2 * block_n), u2);
+  tmem_ld16(taddr + (uint32_t)(n_main * block_n), uc);
+  tmem_ld_wait();
+  if (used > 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(u1[i])));
+  }
+  if (used > 2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(u2[i])));
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(uc[i])));
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64).
 // Rows are 128 B apart, 8-row swizzle atoms 1024 B apart (SBO).
@@ -243,19 +271,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const size_t head_row = g.is_head ? (size_t)f * g.num_anchors + g.row_off + (size_t)(m - f * g.hw) * g.anchors_per_loc : 0;
     for (int c0 = 0; c0 < g.block_n; c0 += 16) {
       uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (X3) {
-        const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
-        for (int a = 1; a <= g.n_main; ++a) {
-          if (a < g.n_main && a >= used) continue;  // accumulator never written (very small K)
-          uint32_t u[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * g.block_n + c0), u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])));
-        }
-      }
+      load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
+                     min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
       const int n = n0 + c0;
       if (m >= g.M || n >= g.N) continue;
       if (g.splits > 1) {
@@ -482,18 +499,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
 #pragma unroll
         for (int h = 0; h < CW / 16; ++h) {
           uint32_t v[16];
-          tmem_ld16(acc0 + (uint32_t)(c0 + h * 16), v);
-          tmem_ld_wait();
-          if (X3) {
-            for (int a = 1; a <= g.n_main; ++a) {
-              if (a < g.n_main && a >= used) continue;
-              uint32_t u[16];
-              tmem_ld16(acc0 + (uint32_t)(a * g.block_n + c0 + h * 16), u);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(u[i])));
-            }
-          }
+          load_acc16<X3>(acc0 + (uint32_t)(c0 + h * 16), g.block_n, g.n_main, used, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int nn = n0 + c0 + h * 16 + i;
@@ -771,6 +777,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
                  g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
   if (persist && mode == TC_TF32X3) {
     g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
+    if (g.k_blocks * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;  // short chains: no measurable bias
     if (2 * (g.n_main + 1) * g.block_n > 512) persist = false;
   }
   if (persist && mode != TC_TF32X3 && 2 * g.block_n > 512) persist = false;
