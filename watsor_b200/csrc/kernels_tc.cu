@@ -762,7 +762,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.partial = partial;
   const long tiles = (long)grid.x * grid.y;
   if (partial != nullptr && tiles < 74 && g.k_blocks >= 4) {
-    int want = (int)((148 + tiles - 1) / tiles);
+    int want = (int)((148 + tiles - 1) / tiles);  // ~one CTA per SM of a B200
     int splits = std::min(want, g.k_blocks / 2);
     while (splits > 1 && (size_t)splits * g.M * g.n_pad > partial_floats) --splits;
     if (splits > 1) {
@@ -773,7 +773,14 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   }
   // many-tile layers: persistent kernel (double-buffered TMEM, TMA-store epilogue)
   const int cw = mode == TC_BF16 ? 64 : 32;
-  bool persist = !g.is_head && g.splits == 1 && tiles >= 148 && g.N == g.n_pad && g.block_n % cw == 0 &&
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  bool persist = !g.is_head && g.splits == 1 && tiles >= num_sms && g.N == g.n_pad && g.block_n % cw == 0 &&
                  g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
   if (persist && mode == TC_TF32X3) {
     g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
@@ -821,7 +828,13 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     CUtensorMap map_out;
     if (!make_out_map(&map_out, out, elem, g.M, g.N, err)) return 1;
     const int idx = 3 + (mode == TC_BF16 ? 0 : (mode == TC_TF32X1 ? 1 : 2));
-    dim3 pgrid((unsigned)std::min<long>(tiles, 148));
+    static int persist_ctas = 0;
+    if (persist_ctas == 0) {
+      const char* e = getenv("WB_PERSIST_CTAS");
+      persist_ctas = e ? atoi(e) : num_sms;
+      if (persist_ctas <= 0 || persist_ctas > num_sms) persist_ctas = num_sms;
+    }
+    dim3 pgrid((unsigned)std::min<long>(tiles, persist_ctas));
     if (mode == TC_BF16) {
       if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       k_gemm_tc_persist<0><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
