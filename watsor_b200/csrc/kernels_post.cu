@@ -32,36 +32,56 @@ __device__ __forceinline__ float sigmoid_score(float logit, float logit_scale) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z)));
 }
 
-constexpr int DEC_TILE = 128;
+constexpr int DEC_TILE = 64;
 
 // grid (ceil(N/DEC_TILE), frames).  Decodes DEC_TILE boxes, then sweeps the [DEC_TILE][C+1] logit tile
-// with coalesced loads; every (anchor, class) with score > threshold is appended to the candidate
-// list of (frame, class) as key = score_bits << 32 | ~anchor  (sorting keys descending gives
-// "score descending, lower anchor index first", the pop order of TF's NonMaxSuppressionV5).
+// with coalesced loads; every (anchor, class) with score > threshold becomes a candidate key
+// score_bits << 32 | ~anchor  (sorting keys descending gives "score descending, lower anchor index first",
+// the pop order of TF's NonMaxSuppressionV5).  Appends are aggregated per block: positions inside the
+// block come from shared-memory counters, one global atomicAdd per (block, class) reserves the range
+// (90 classes x 1917 anchors would otherwise be 172 k global atomics per frame on 90 addresses).
 __global__ void __launch_bounds__(256)
     k_decode_scores(PostParams pp, const float* __restrict__ enc, const float* __restrict__ logits,
                     const float* __restrict__ anchors, float4* __restrict__ dec, int* __restrict__ cand_count,
                     unsigned long long* __restrict__ cand) {
+  extern __shared__ unsigned char s_dec_raw[];
   const int f = blockIdx.y, a0 = blockIdx.x * DEC_TILE;
   const int N = pp.num_anchors, C = pp.num_classes, C1 = C + 1;
   const int na = min(DEC_TILE, N - a0);
+  const int total = na * C1;
+  float* s_score = reinterpret_cast<float*>(s_dec_raw);                         // [DEC_TILE*C1]
+  int* s_cnt = reinterpret_cast<int*>(s_score + DEC_TILE * C1);                 // [C] then base [C]
+  int* s_base = s_cnt + C;
+  short* s_pos = reinterpret_cast<short*>(s_base + C);                          // [DEC_TILE*C1]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = 0;
   if ((int)threadIdx.x < na) {
     int i = a0 + threadIdx.x;
     float4 e = reinterpret_cast<const float4*>(enc)[(size_t)f * N + i];
     float4 a = reinterpret_cast<const float4*>(anchors)[i];
     dec[(size_t)f * N + i] = decode_box(e, a, pp);
   }
+  __syncthreads();
   const float* lt = logits + ((size_t)f * N + a0) * C1;
-  const int total = na * C1;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     int il = e / C1, c = e - il * C1;
-    if (c == 0) continue;  // `Postprocessor/Slice`: background column dropped after the sigmoid
-    float s = sigmoid_score(lt[e], pp.logit_scale);
-    if (s > pp.score_thr) {
-      int pos = atomicAdd(&cand_count[f * C + (c - 1)], 1);
-      cand[((size_t)f * C + (c - 1)) * N + pos] =
-          ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(a0 + il));
+    short pos = -1;
+    if (c != 0) {  // `Postprocessor/Slice`: background column dropped after the sigmoid
+      float sc = sigmoid_score(lt[e], pp.logit_scale);
+      s_score[e] = sc;
+      if (sc > pp.score_thr) pos = (short)atomicAdd(&s_cnt[c - 1], 1);
     }
+    s_pos[e] = pos;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    s_base[c] = s_cnt[c] > 0 ? atomicAdd(&cand_count[f * C + c], s_cnt[c]) : 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const short pos = s_pos[e];
+    if (pos < 0) continue;
+    int il = e / C1, c = e - il * C1;
+    cand[((size_t)f * C + (c - 1)) * N + s_base[c - 1] + pos] =
+        ((unsigned long long)__float_as_uint(s_score[e]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(a0 + il));
   }
 }
 
@@ -81,22 +101,83 @@ __device__ __forceinline__ float iou_tf(float4 bi, float4 bj) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
 }
 
+// Same predicate as `iou_tf(a, b) > thr` for boxes whose corners were normalised (min/max) and whose areas
+// were computed once: disjoint boxes are rejected after 4 min/max + 2 subtractions, without the IEEE
+// division.  inter = max(dy,0)*max(dx,0) is 0 when dy <= 0 or dx <= 0, so IoU is 0 <= thr there.
+struct NBox {
+  float4 c;  // ymin, xmin, ymax, xmax (normalised)
+  float area;
+};
+__device__ __forceinline__ NBox normalise_box(float4 b) {
+  NBox r;
+  r.c = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+  r.area = __fmul_rn(__fsub_rn(r.c.z, r.c.x), __fsub_rn(r.c.w, r.c.y));
+  return r;
+}
+__device__ __forceinline__ bool suppresses(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  const float iy0 = fmaxf(a.x, b.x), ix0 = fmaxf(a.y, b.y), iy1 = fminf(a.z, b.z), ix1 = fminf(a.w, b.w);
+  const float dy = __fsub_rn(iy1, iy0), dx = __fsub_rn(ix1, ix0);
+  if (!(dy > 0.f && dx > 0.f)) return false;
+  if (area_a <= 0.f || area_b <= 0.f) return false;
+  const float inter = __fmul_rn(dy, dx);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
+}
+
 __device__ __forceinline__ float4 clip_unit(float4 b) {  // ClipToWindow [0,0,1,1]
   return make_float4(fmaxf(fminf(b.x, 1.f), 0.f), fmaxf(fminf(b.y, 1.f), 0.f), fmaxf(fminf(b.z, 1.f), 0.f),
                      fmaxf(fminf(b.w, 1.f), 0.f));
 }
 
-// grid (classes, frames), 256 threads.  Bitonic sort of the candidate keys in shared memory, then
-// warp 0 runs the greedy suppression: 32 candidates are fetched per round, each is tested against
-// the kept boxes (<= 128, in shared memory) by all lanes at once and a ballot decides.
-// Output: merge keys  score_bits << 32 | (0xFFFF - class) << 16 | (0xFFFF - rank)  for the kept
-// boxes whose window-clipped area is positive (0 otherwise), plus the anchor index of every kept box.
+// descending bitonic sort of P (power of two) keys in shared memory, whole block
+__device__ __forceinline__ void bitonic_desc(unsigned long long* a, int P) {
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? x < y : x > y) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// grid (classes, frames), 256 threads.  Per (frame, class):
+//  1. candidate keys -> shared memory.  With many candidates (score threshold 1e-8 makes every anchor one)
+//     only the head of the order is ever visited before max_per_class boxes are kept, so the keys are first
+//     split by a score histogram (11 bits of the float) into a "high" segment of >= NMS_HEAD keys and the
+//     rest; the high segment is sorted (bitonic), the rest only if the greedy pass runs out of candidates.
+//     Every key of the high segment is larger than every key of the rest, so the visiting order is unchanged.
+//  2. greedy suppression with exact sequential semantics, 32 candidates per round:
+//     phase 1 (all 8 warps): candidate i vs every box kept in EARLIER rounds (warp w takes candidates
+//     4w..4w+3, lanes stride over the kept list, a ballot decides);
+//     phase 2 (warp 0): walk the 32 candidates in order; a surviving candidate is kept and immediately
+//     suppresses the later candidates of the same round that it overlaps.
+// Output: merge keys  score_bits << 32 | (0xFFFF - class) << 16 | (0xFFFF - rank)  for the kept boxes whose
+// window-clipped area is positive (0 otherwise), plus the anchor index of every kept box.
+constexpr int NMS_HEAD = 384;
+constexpr int NMS_PREFILTER_MIN = 640;
+
 __global__ void __launch_bounds__(256)
     k_nms(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ cand_count,
           const unsigned long long* __restrict__ cand, int sort_cap, int* __restrict__ sel_count,
           unsigned long long* __restrict__ sel_key, int* __restrict__ sel_idx) {
-  extern __shared__ unsigned long long s_keys[];  // [sort_cap]
-  __shared__ float4 s_kept[128];
+  extern __shared__ unsigned long long s_dyn[];  // [2][sort_cap]: high segment, low segment
+  unsigned long long* s_a = s_dyn;
+  unsigned long long* s_b = s_dyn + sort_cap;
+  __shared__ float4 s_kept[128];  // normalised corners of the kept boxes
+  __shared__ float s_karea[128];
+  __shared__ float4 s_cbox[32];  // normalised corners of the round's candidates
+  __shared__ float s_carea[32];
+  __shared__ float4 s_craw[32];  // as decoded (for the clipped-area test)
+  __shared__ unsigned s_alive;   // bit i: candidate i of the round survived phase 1
+  __shared__ int s_nkept_sh, s_na, s_nb, s_cut;
+  __shared__ int s_hist[1024];
   const int c = blockIdx.x, f = blockIdx.y, C = pp.num_classes, N = pp.num_anchors;
   const int n = min(cand_count[f * C + c], N);
   const int max_out = min(pp.max_per_class, N);
@@ -107,61 +188,142 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) sel_count[f * C + c] = 0;
     return;
   }
-  int P = 32;
-  while (P < n) P <<= 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long* ck = cand + ((size_t)f * C + c) * N;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? ck[i] : 0ull;
+  int n_a = n, n_b = 0;
+  if (n <= NMS_PREFILTER_MIN) {
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_a[i] = i < n ? ck[i] : 0ull;
+    __syncthreads();
+    bitonic_desc(s_a, P);
+  } else {
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_na = s_nb = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = ck[i];
+      atomicAdd(&s_hist[min((int)(k >> 52), 1023)], 1);  // sign + exponent + 3 mantissa bits of the score
+    }
+    __syncthreads();
+    if (warp == 0) {  // highest bins first until NMS_HEAD keys are covered
+      int acc = 0, cut = 0;
+      for (int top = 1023; top >= 0 && acc < NMS_HEAD; top -= 32) {
+        const int b = top - lane;
+        const int v = b >= 0 ? s_hist[b] : 0;
+        int incl = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned reach = __ballot_sync(0xffffffffu, acc + incl >= NMS_HEAD);
+        if (reach) {
+          const int l = __ffs(reach) - 1;
+          cut = top - l;
+          acc += __shfl_sync(0xffffffffu, incl, l);
+          break;
+        }
+        acc += __shfl_sync(0xffffffffu, incl, 31);
+        cut = max(top - 31, 0);
+      }
+      if (lane == 0) s_cut = cut;
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = ck[i];  // second pass over the L2-resident keys
+      if (min((int)(k >> 52), 1023) >= cut)
+        s_a[atomicAdd(&s_na, 1)] = k;
+      else
+        s_b[atomicAdd(&s_nb, 1)] = k;
+    }
+    __syncthreads();
+    n_a = s_na;
+    n_b = s_nb;
+    int P = 32;
+    while (P < n_a) P <<= 1;
+    for (int i = n_a + threadIdx.x; i < P; i += blockDim.x) s_a[i] = 0ull;
+    __syncthreads();
+    bitonic_desc(s_a, P);
+  }
+
+  const float4* fdec = dec + (size_t)f * N;
+  if (threadIdx.x == 0) s_nkept_sh = 0;
   __syncthreads();
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          unsigned long long a = s_keys[i], b = s_keys[ixj];
-          bool desc = (i & k) == 0;  // descending overall
-          if (desc ? a < b : a > b) {
-            s_keys[i] = b;
-            s_keys[ixj] = a;
-          }
+  for (int seg = 0; seg < 2; ++seg) {
+    const unsigned long long* sorted = seg == 0 ? s_a : s_b;
+    const int count = seg == 0 ? n_a : n_b;
+    if (seg == 1) {
+      if (count == 0 || s_nkept_sh >= max_out) break;  // uniform: s_nkept_sh was published before a barrier
+      int P = 32;
+      while (P < count) P <<= 1;
+      for (int i = count + threadIdx.x; i < P; i += blockDim.x) s_b[i] = 0ull;
+      __syncthreads();
+      bitonic_desc(s_b, P);
+    }
+    for (int base = 0; base < count; base += 32) {
+      const int nkept = s_nkept_sh;
+      if (nkept >= max_out) break;
+      const int cnt = min(32, count - base);
+      if (threadIdx.x < 32) {
+        if (lane < cnt) {
+          const unsigned idx = 0xFFFFFFFFu - (unsigned)(sorted[base + lane] & 0xFFFFFFFFull);
+          const float4 raw = fdec[idx];
+          const NBox nb = normalise_box(raw);
+          s_craw[lane] = raw;
+          s_cbox[lane] = nb.c;
+          s_carea[lane] = nb.area;
+        }
+        if (lane == 0) s_alive = 0u;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = warp * 4 + k;
+        if (i < cnt) {
+          const float4 bi = s_cbox[i];
+          const float ai = s_carea[i];
+          bool sup = false;
+          for (int j = lane; j < nkept; j += 32) sup |= suppresses(bi, ai, s_kept[j], s_karea[j], pp.iou_thr);
+          if (!__any_sync(0xffffffffu, sup) && lane == 0) atomicOr(&s_alive, 1u << i);
         }
       }
       __syncthreads();
-    }
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  const float4* fdec = dec + (size_t)f * N;
-  int nkept = 0;
-  for (int base = 0; base < n && nkept < max_out; base += 32) {
-    int my = base + lane;
-    unsigned long long key = my < n ? s_keys[my] : 0ull;
-    unsigned idx = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-    float4 box = my < n ? fdec[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    int cnt = min(32, n - base);
-    for (int t = 0; t < cnt && nkept < max_out; ++t) {
-      float4 bi;
-      bi.x = __shfl_sync(0xffffffffu, box.x, t);
-      bi.y = __shfl_sync(0xffffffffu, box.y, t);
-      bi.z = __shfl_sync(0xffffffffu, box.z, t);
-      bi.w = __shfl_sync(0xffffffffu, box.w, t);
-      bool sup = false;
-      for (int j = lane; j < nkept; j += 32) sup |= iou_tf(bi, s_kept[j]) > pp.iou_thr;
-      if (!__any_sync(0xffffffffu, sup)) {
-        if (lane == t) {
-          s_kept[nkept] = box;
-          float4 cb = clip_unit(box);
-          float area = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
-          out_idx[nkept] = (int)idx;
-          out_key[nkept] = area > 0.f ? ((key & 0xFFFFFFFF00000000ull) |
-                                         ((unsigned long long)(0xFFFFu - (unsigned)c) << 16) |
-                                         (unsigned long long)(0xFFFFu - (unsigned)nkept))
-                                      : 0ull;
+      if (warp == 0) {
+        unsigned alive = s_alive;
+        const float4 box = lane < cnt ? s_cbox[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float barea = lane < cnt ? s_carea[lane] : 0.f;
+        int nk = nkept;
+        for (int t = 0; t < cnt && nk < max_out; ++t) {
+          if (!((alive >> t) & 1u)) continue;  // warp-uniform
+          float4 bt;
+          bt.x = __shfl_sync(0xffffffffu, box.x, t);
+          bt.y = __shfl_sync(0xffffffffu, box.y, t);
+          bt.z = __shfl_sync(0xffffffffu, box.z, t);
+          bt.w = __shfl_sync(0xffffffffu, box.w, t);
+          const float at = __shfl_sync(0xffffffffu, barea, t);
+          if (lane == t) {
+            const unsigned long long key = sorted[base + t];
+            s_kept[nk] = box;
+            s_karea[nk] = barea;
+            float4 cb = clip_unit(s_craw[t]);
+            float area = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
+            out_idx[nk] = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            out_key[nk] = area > 0.f ? ((key & 0xFFFFFFFF00000000ull) | ((unsigned long long)(0xFFFFu - (unsigned)c) << 16) |
+                                        (unsigned long long)(0xFFFFu - (unsigned)nk))
+                                     : 0ull;
+          }
+          ++nk;
+          const bool hit = lane > t && lane < cnt && suppresses(box, barea, bt, at, pp.iou_thr);
+          alive &= ~__ballot_sync(0xffffffffu, hit);
         }
-        ++nkept;
-        __syncwarp();
+        if (lane == 0) s_nkept_sh = nk;
       }
+      __syncthreads();
     }
   }
-  if (lane == 0) sel_count[f * C + c] = nkept;
+  if (threadIdx.x == 0) sel_count[f * C + c] = s_nkept_sh;
 }
 
 // ------------------------------------------------------------------------------------------- K9
@@ -236,7 +398,7 @@ __device__ uint32_t apply_filters(const CameraCfg* __restrict__ cam, wb_detectio
 // merge of the per-class sorted lists = `SortByField` (TopKV2, ties -> lower concat index) restricted
 // to boxes with positive clipped area, top max_total; (3) one thread per output row: clip, `add` +1,
 // tensorflow_cpu.py:79-90 integer conversion, predicates, Detection write.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     k_merge_filter(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ sel_count,
                    const unsigned long long* __restrict__ sel_key, const int* __restrict__ sel_idx,
                    const FrameDesc* __restrict__ frames, const CameraCfg* __restrict__ cams, uint32_t flags,
@@ -247,7 +409,19 @@ __global__ void __launch_bounds__(128)
   __shared__ int s_nvalid;
   const int f = blockIdx.x, C = pp.num_classes, MP = pp.max_per_class, N = pp.num_anchors;
   const unsigned long long* keys = sel_key + (size_t)f * C * MP;
-  for (int i = threadIdx.x; i < C * MP; i += blockDim.x) s_all[i] = keys[i];
+  {
+    const int total = C * MP;
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < total; i += 4 * blockDim.x) {  // 4 independent loads in flight per thread
+      const unsigned long long k0 = keys[i], k1 = keys[i + blockDim.x], k2 = keys[i + 2 * blockDim.x],
+                               k3 = keys[i + 3 * blockDim.x];
+      s_all[i] = k0;
+      s_all[i + blockDim.x] = k1;
+      s_all[i + 2 * blockDim.x] = k2;
+      s_all[i + 3 * blockDim.x] = k3;
+    }
+    for (; i < total; i += blockDim.x) s_all[i] = keys[i];
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -267,8 +441,12 @@ __global__ void __launch_bounds__(128)
         int c = lane + 32 * t;
         if (ptr[t] < cnt[t]) best = max(best, s_all[c * MP + ptr[t]]);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+      // 64-bit max over the warp as two 32-bit hardware reductions: the score word first, then the
+      // (class, rank) word among the lanes that hold the winning score
+      const unsigned hi = (unsigned)(best >> 32);
+      const unsigned m_hi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned m_lo = __reduce_max_sync(0xffffffffu, hi == m_hi ? (unsigned)best : 0u);
+      best = ((unsigned long long)m_hi << 32) | m_lo;
       if (best == 0ull) break;
       int c = 0xFFFF - (int)((best >> 16) & 0xFFFFull);
       if ((c & 31) == lane) {
@@ -330,8 +508,9 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
   const int C = pp.num_classes, N = pp.num_anchors;
   cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)n * C, lc.stream);
   dim3 g1((N + DEC_TILE - 1) / DEC_TILE, n);
-  k_decode_scores<<<g1, 256, 0, lc.stream>>>(pp, enc, logits, anchors, reinterpret_cast<float4*>(dec_boxes),
-                                             cand_count, cand);
+  const size_t dec_smem = (size_t)DEC_TILE * (C + 1) * (sizeof(float) + sizeof(short)) + 2 * sizeof(int) * C + 16;
+  k_decode_scores<<<g1, 256, dec_smem, lc.stream>>>(pp, enc, logits, anchors, reinterpret_cast<float4*>(dec_boxes),
+                                                    cand_count, cand);
   ++*lc.launch_counter;
   int sort_cap = 32;
   while (sort_cap < N) sort_cap <<= 1;
@@ -341,13 +520,14 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_decode_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
-  k_nms<<<dim3(C, n), 256, sizeof(unsigned long long) * sort_cap, lc.stream>>>(
+  k_nms<<<dim3(C, n), 256, 2 * sizeof(unsigned long long) * sort_cap, lc.stream>>>(
       pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx);
   ++*lc.launch_counter;
-  k_merge_filter<<<n, 128, sizeof(unsigned long long) * (size_t)C * pp.max_per_class, lc.stream>>>(
+  k_merge_filter<<<n, 256, sizeof(unsigned long long) * (size_t)C * pp.max_per_class, lc.stream>>>(
       pp, reinterpret_cast<const float4*>(dec_boxes), sel_count, sel_key, sel_idx, frames, cams, flags, out,
       verdicts, raw_boxes, raw_scores, raw_classes, raw_num);
   ++*lc.launch_counter;

@@ -166,6 +166,7 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   REQUIRE(c->hdr.max_per_class >= 1 && c->hdr.max_per_class <= 128, "max_per_class must be in 1..128");
   REQUIRE(c->hdr.max_total >= 1 && c->hdr.max_total <= 128, "max_total must be in 1..128");
   REQUIRE(c->hdr.score_thr >= 0.f, "negative score threshold is not supported");
+  REQUIRE(c->hdr.iou_thr >= 0.f, "negative IoU threshold is not supported");
   REQUIRE(c->hdr.num_anchors >= 1 && c->hdr.num_anchors <= 16384, "num_anchors out of range");
   for (auto& L : c->layers) {
     if (L.op == WB_OP_PW || L.op == WB_OP_HEAD)
