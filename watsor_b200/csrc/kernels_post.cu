@@ -519,7 +519,7 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
   int* sel_idx = reinterpret_cast<int*>(sel + (size_t)n * C * pp.max_per_class);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
     cudaFuncSetAttribute(k_decode_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;

@@ -174,6 +174,104 @@ __global__ void __launch_bounds__(ST_TY* ST_TX)
   }
 }
 
+// Register-tiled variant for the common 3x3 / stride-2 / 32-channel stem: one thread = 4 consecutive output
+// pixels x 8 output channels, so every weight vector read from shared memory feeds 4 pixels (the generic
+// kernel re-reads all 27x32 weights per pixel: `LDS.128` broadcasts cost 4 wavefronts each and dominated).
+// Same tile (8 x 32 pixels), same resize code, same (ky, kx, c) accumulation order => identical results.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_stem_3x3s2_c32(const FrameDesc* __restrict__ frames, const float* __restrict__ pre, wb_layer L, int in_h, int in_w,
+                     float mul, float sub, const float* __restrict__ w, const float* __restrict__ scale,
+                     const float* __restrict__ offset, T* __restrict__ out) {
+  constexpr int K = 3, S = 2, OC = 32;
+  constexpr int tile_h = (ST_TY - 1) * S + K, tile_w = (ST_TX - 1) * S + K;  // 17 x 65
+  __shared__ __align__(16) float s_in[tile_h * tile_w * 3];
+  __shared__ __align__(16) float s_w[K * K * 3 * OC];
+  const int f = blockIdx.z;
+  const int oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * K * 3 * OC; i += 256) s_w[i] = w[(i / OC) * L.n_pad + (i % OC)];
+  const int ry0 = oy0 * S - (int)L.pad_t, rx0 = ox0 * S - (int)L.pad_l;
+  FrameDesc fd;
+  float sy = 1.f, sx = 1.f;
+  if (pre == nullptr) {
+    fd = frames[f];
+    sy = axis_scale(fd.h, in_h);
+    sx = axis_scale(fd.w, in_w);
+  }
+  for (int i = tid; i < tile_h * tile_w; i += 256) {
+    int ly = i / tile_w, lx = i - ly * tile_w;
+    int ry = ry0 + ly, rx = rx0 + lx;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ry >= 0 && ry < in_h && rx >= 0 && rx < in_w) {
+      if (pre != nullptr) {
+        const float* p = pre + (((size_t)f * in_h + ry) * in_w + rx) * 3;
+        v[0] = p[0];
+        v[1] = p[1];
+        v[2] = p[2];
+      } else {
+        AxisTap ty = axis_tap(ry, fd.h, sy), tx = axis_tap(rx, fd.w, sx);
+        resized_pixel(fd.ptr, fd.w, ty, tx, mul, sub, v);
+      }
+    }
+    s_in[i * 3 + 0] = v[0];
+    s_in[i * 3 + 1] = v[1];
+    s_in[i * 3 + 2] = v[2];
+  }
+  __syncthreads();
+
+  const int ocg = tid & 3, quad = tid >> 2;  // 4 channel groups of 8, 64 pixel quads (8 rows x 8 quads)
+  const int ty = quad >> 3, tx0 = (quad & 7) * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[((ky * K + kx) * 3 + c) * OC + ocg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[((ky * K + kx) * 3 + c) * OC + ocg * 8 + 4]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float x = s_in[((ty * S + ky) * tile_w + (tx0 + o) * S + kx) * 3 + c];
+          acc[o][0] = fmaf(x, w0.x, acc[o][0]);
+          acc[o][1] = fmaf(x, w0.y, acc[o][1]);
+          acc[o][2] = fmaf(x, w0.z, acc[o][2]);
+          acc[o][3] = fmaf(x, w0.w, acc[o][3]);
+          acc[o][4] = fmaf(x, w1.x, acc[o][4]);
+          acc[o][5] = fmaf(x, w1.y, acc[o][5]);
+          acc[o][6] = fmaf(x, w1.z, acc[o][6]);
+          acc[o][7] = fmaf(x, w1.w, acc[o][7]);
+        }
+      }
+  const int oy = oy0 + ty;
+  if (oy >= (int)L.out_h) return;
+  float sc[8], of[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + ocg * 8 + j);
+    of[j] = __ldg(offset + ocg * 8 + j);
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int ox = ox0 + tx0 + o;
+    if (ox >= (int)L.out_w) break;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = affine_rn(acc[o][j], sc[j], of[j]);
+      y[j] = L.act == WB_ACT_RELU6 ? relu6f(v) : v;
+    }
+    T* dst = out + (((size_t)f * L.out_h + oy) * L.out_w + ox) * OC + ocg * 8;
+    ActIO<T>::st4(dst, make_float4(y[0], y[1], y[2], y[3]));
+    ActIO<T>::st4(dst + 4, make_float4(y[4], y[5], y[6], y[7]));
+  }
+}
+
 template <typename T>
 void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre, int n, const wb_layer& L,
                  int in_h, int in_w, float mul, float sub, const float* w, const float* scale,
@@ -181,6 +279,11 @@ void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre,
   const int tile_h = (ST_TY - 1) * L.stride + L.kh, tile_w = (ST_TX - 1) * L.stride + L.kw;
   size_t smem = ((((size_t)tile_h * tile_w * 3 + 3) & ~(size_t)3) + (size_t)L.kh * L.kw * 3 * L.n_pad) * sizeof(float);
   dim3 grid((L.out_w + ST_TX - 1) / ST_TX, (L.out_h + ST_TY - 1) / ST_TY, n);
+  if (L.kh == 3 && L.kw == 3 && L.stride == 2 && L.out_c == 32) {
+    k_stem_3x3s2_c32<T><<<grid, 256, 0, lc.stream>>>(frames, pre, L, in_h, in_w, mul, sub, w, scale, offset, out);
+    ++*lc.launch_counter;
+    return;
+  }
   static bool attr_done = false;
   if (!attr_done && smem > 48 * 1024) {
     cudaFuncSetAttribute(k_stem<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -167,7 +167,7 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   REQUIRE(c->hdr.max_total >= 1 && c->hdr.max_total <= 128, "max_total must be in 1..128");
   REQUIRE(c->hdr.score_thr >= 0.f, "negative score threshold is not supported");
   REQUIRE(c->hdr.iou_thr >= 0.f, "negative IoU threshold is not supported");
-  REQUIRE(c->hdr.num_anchors >= 1 && c->hdr.num_anchors <= 16384, "num_anchors out of range");
+  REQUIRE(c->hdr.num_anchors >= 1 && c->hdr.num_anchors <= 8192, "num_anchors must be in 1..8192 (NMS sort buffers live in shared memory)");
   for (auto& L : c->layers) {
     if (L.op == WB_OP_PW || L.op == WB_OP_HEAD)
       REQUIRE(L.in_c % 4 == 0, std::string("layer ") + L.name + ": in_c must be a multiple of 4");
