@@ -52,3 +52,28 @@ def test_pointwise_gemm(precision, rel_tol, K, N, hw, n):
     ref = np.clip(ref * sc.astype(np.float64) + of.astype(np.float64), 0.0, 6.0)
     err = np.abs(y.reshape(-1, N) - ref).max()
     assert err <= rel_tol * max(1.0, np.abs(ref).max()) * (4 if precision == 1 else 1), (err, np.abs(ref).max())
+
+
+def test_fused_depthwise_pointwise_equals_unfused(shapes_model):
+    """k_dwpw_tc_x3 (depthwise fused into the GEMM's A-operand producer, csrc/kernels_fused.cu) against
+    the two-kernel path (WB_NO_FUSE=1): same accumulation orders, so the head outputs are bit-identical."""
+    import os
+    from tests.artist import artist_frame
+    from oracle.ssd_model import SsdModelOracle
+    oracle = SsdModelOracle(shapes_model)
+    pres = np.stack([oracle.preprocess(artist_frame(640, 480, 3, f)) for f in range(4)])
+    outs = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            os.environ['WB_NO_FUSE'] = '1'
+        else:
+            os.environ.pop('WB_NO_FUSE', None)
+        try:
+            with Engine(shapes_model.to_blob(), device=0, max_batch=4, precision=2) as e:
+                enc, lg, _ = e.backbone(pres)
+                launches = e.last_launch_count()
+        finally:
+            os.environ.pop('WB_NO_FUSE', None)
+        outs.append((enc, lg, launches))
+    assert outs[0][2] < outs[1][2]                      # fewer launches: pairs really were fused
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])

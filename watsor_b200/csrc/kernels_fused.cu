@@ -1,0 +1,416 @@
+// kernels_fused.cu -- depthwise 3x3 conv (+BN+ReLU6) fused into the A-operand producer of the tensor-core
+// 1x1 conv (+BN+ReLU6): the depthwise activation never exists in HBM (K3+K4 of SURVEY.md 2.2).
+//
+// Restates the layer pairs `Conv2d_i_depthwise` -> `Conv2d_i_pointwise` of the frozen graph
+// (watsor/detection/tensorflow_cpu.py:114 runs them inside sess.run).  fp32-faithful mode only (TF32X3).
+//
+// Persistent kernel, one CTA per SM, output tile = 8 x 16 pixels of one image x all N (<= 128) channels:
+//   warp 0      TMA producer: per 32-channel k-block a 4-D box {32 ch, halo_w, halo_h, 1 image} of the
+//               depthwise INPUT (halo included; out-of-image coordinates are zero-filled by TMA = TF SAME
+//               padding) and the 1x1 weight tiles (hi, lo)
+//   warps 6..13 depthwise producers: 3x3 taps from the halo tile in shared memory (8 lanes = the 8 channel
+//               quads of one pixel -> conflict-free 128-byte rows, the 9 tap weights live in registers),
+//               BN + ReLU6, TF32 hi/lo split, written straight into the 128B-swizzled UMMA A tiles
+//   warp 1      tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
+//   warps 2..5  epilogue: tcgen05.ld -> BN + ReLU6 -> swizzled staging -> 4-D TMA store {32 ch, 16, 2, 1}
+// The depthwise accumulation order (ky, kx) and the GEMM's k order are those of the unfused kernels, so
+// the result is bit-identical to running k_dw_strip followed by k_gemm_tc_persist.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels_tc.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int F_TH = 8, F_TW = 16;  // output tile (pixels) = 128 GEMM rows
+constexpr int F_STAGING_BYTES = 4 * 2 * 4096;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+struct FusedArgs {
+  const float* dw_w;  // [9][C]
+  const float* dw_scale;
+  const float* dw_offset;
+  const float* scale;  // 1x1 layer, [n_pad]
+  const float* offset;
+  int dw_act, act;
+  int C, S, pad_t, pad_l;
+  int OH, OW, n_img;
+  int N, block_n, k_blocks, n_main;
+  int tiles_x, tiles_y;
+  int stages, halo_stages;
+  int th_in, tw_in;
+};
+
+__global__ void __launch_bounds__(448, 1)
+    k_dwpw_tc_x3(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out, FusedArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int halo_bytes = ((g.th_in * g.tw_in * ROW_BYTES + 1023) / 1024) * 1024;
+  const int b_tile_bytes = g.block_n * ROW_BYTES;
+  const int ab_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  uint8_t* halo0 = smem;
+  uint8_t* ab0 = halo0 + (size_t)g.halo_stages * halo_bytes;
+  uint8_t* staging = ab0 + (size_t)g.stages * ab_bytes;
+  uint64_t* halo_full = reinterpret_cast<uint64_t*>(staging + F_STAGING_BYTES);
+  uint64_t* halo_empty = halo_full + g.halo_stages;
+  uint64_t* b_full = halo_empty + g.halo_stages;
+  uint64_t* a_ready = b_full + g.stages;
+  uint64_t* empty = a_ready + g.stages;
+  uint64_t* acc_full = empty + g.stages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int num_tiles = tiles_per_img * g.n_img;
+  const int n_acc = g.n_main + 1;
+  const int set_cols = n_acc * g.block_n;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * set_cols) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int h = 0; h < g.halo_stages; ++h) {
+      mbar_init(smem_u32(&halo_full[h]), 1);
+      mbar_init(smem_u32(&halo_empty[h]), 8);  // one arrive per depthwise producer warp
+    }
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&a_ready[s]), 8);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+        const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const int h = it % g.halo_stages, s = it % g.stages;
+          mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
+          const uint32_t hb = smem_u32(&halo_full[h]);
+          mbar_expect_tx(hb, (uint32_t)(g.th_in * g.tw_in * ROW_BYTES));
+          tma_load_4d(smem_u32(halo0 + (size_t)h * halo_bytes), &map_in, hb, kb * 32, ox0 * g.S - g.pad_l,
+                      oy0 * g.S - g.pad_t, img);
+          mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
+          const uint32_t bb = smem_u32(&b_full[s]);
+          uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;
+          mbar_expect_tx(bb, 2 * b_tile_bytes);
+          tma_load_2d(smem_u32(sb), &map_b, bb, kb * 32, 0);
+          tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bb, kb * 32, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(true, BLOCK_M, g.block_n);
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * set_cols);
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
+        mbar_wait(smem_u32(&a_ready[s]), ph);
+        mbar_wait(smem_u32(&b_full[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          uint8_t* st = ab0 + (size_t)s * ab_bytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+            const uint32_t koff = k * UMMA_K_BYTES;
+            const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+            const uint32_t d_main = acc0 + (uint32_t)((step % g.n_main) * g.block_n);
+            const uint32_t d_corr = acc0 + (uint32_t)(g.n_main * g.block_n);
+            umma<true>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
+            umma<true>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+            umma<true>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty[s]));
+          if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    uint8_t* my_stage = staging + (size_t)q * 2 * 4096;
+    const int used = min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES));
+    int j = 0, chunk_no = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+      const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
+      mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
+      for (int c0 = 0; c0 < g.block_n; c0 += 32, ++chunk_no) {
+        float y[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[16];
+          load_acc16<true>(acc0 + (uint32_t)(c0 + hh * 16), g.block_n, g.n_main, used, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int nn = c0 + hh * 16 + i;
+            float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
+            y[hh * 16 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+          }
+        }
+        if (chunk_no >= 2) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* sb = my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 pk;
+          pk.x = __float_as_uint(y[c * 4 + 0]);
+          pk.y = __float_as_uint(y[c * 4 + 1]);
+          pk.z = __float_as_uint(y[c * 4 + 2]);
+          pk.w = __float_as_uint(y[c * 4 + 3]);
+          *reinterpret_cast<uint4*>(sb + ((c ^ (lane & 7)) << 4)) = pk;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          // rows q*32 .. q*32+31 of the tile = spatial rows 2q, 2q+1 (16 pixels each)
+          tma_store_4d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), c0, ox0, oy0 + 2 * q, img);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  } else {
+    // ------------------------------------------------------------------ depthwise producers (8 warps)
+    const int pt = threadIdx.x - 192;      // 0..255
+    const int q = pt & 7, slot = pt >> 3;  // channel quad of the k-block, pixel slot 0..31
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int h = it % g.halo_stages, s = it % g.stages;
+        const int cch = kb * 32 + q * 4;
+        float4 wr[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(g.dw_w + (size_t)k * g.C + cch));
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.dw_scale + cch));
+        const float4 of = __ldg(reinterpret_cast<const float4*>(g.dw_offset + cch));
+        mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
+        mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
+        const float* hal = reinterpret_cast<const float*>(halo0 + (size_t)h * halo_bytes);
+        uint8_t* a_hi = ab0 + (size_t)s * ab_bytes;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = slot + 32 * i;
+          const int ty = r >> 4, tx = r & 15;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float4 x = *reinterpret_cast<const float4*>(
+                  hal + ((size_t)((ty * g.S + ky) * g.tw_in + tx * g.S + kx) * 32 + q * 4));
+              const float4 ww = wr[ky * 3 + kx];
+              acc.x = fmaf(x.x, ww.x, acc.x);
+              acc.y = fmaf(x.y, ww.y, acc.y);
+              acc.z = fmaf(x.z, ww.z, acc.z);
+              acc.w = fmaf(x.w, ww.w, acc.w);
+            }
+          float v[4] = {affine_rn(acc.x, sc.x, of.x), affine_rn(acc.y, sc.y, of.y), affine_rn(acc.z, sc.z, of.z),
+                        affine_rn(acc.w, sc.w, of.w)};
+          uint4 hi, lo;
+          uint32_t* hp = &hi.x;
+          uint32_t* lp = &lo.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = g.dw_act == WB_ACT_RELU6 ? relu6f(v[e]) : v[e];
+            const uint32_t hb = __float_as_uint(a) & 0xFFFFE000u;
+            hp[e] = hb;
+            lp[e] = __float_as_uint(__fsub_rn(a, __uint_as_float(hb))) & 0xFFFFE000u;
+          }
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);  // 128B swizzle
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&a_ready[s]));
+          mbar_arrive(smem_u32(&halo_empty[h]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+struct FusedPlan {
+  int block_n, n_main, stages, halo_stages, th_in, tw_in, tiles_x, tiles_y;
+  size_t smem;
+};
+
+bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
+  p->block_n = pw.n_pad;
+  p->n_main = 1;
+  p->th_in = (F_TH - 1) * dw.stride + 3;
+  p->tw_in = (F_TW - 1) * dw.stride + 3;
+  p->tiles_x = (dw.out_w + F_TW - 1) / F_TW;
+  p->tiles_y = (dw.out_h + F_TH - 1) / F_TH;
+  const size_t halo = ((size_t)p->th_in * p->tw_in * ROW_BYTES + 1023) / 1024 * 1024;
+  const size_t ab = 2 * A_TILE_BYTES + 2 * (size_t)p->block_n * ROW_BYTES;
+  const size_t budget = 225 * 1024 - F_STAGING_BYTES;
+  // prefer two A/B stages, then as many halo buffers as fit (at least two)
+  for (int st = 2; st >= 1; --st)
+    for (int hs = 3; hs >= 2; --hs) {
+      if (hs * halo + st * ab <= budget) {
+        p->stages = st;
+        p->halo_stages = hs;
+        p->smem = hs * halo + st * ab + F_STAGING_BYTES + 1024 + 8 * (2 * hs + 3 * st + 4) + 16;
+        return true;
+      }
+    }
+  return false;
+}
+
+}  // namespace
+
+bool fused_dwpw_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& dw, const wb_layer& pw, int n) {
+  if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr) return false;
+  if (dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
+  if (dw.kh != 3 || dw.kw != 3 || (dw.stride != 1 && dw.stride != 2)) return false;
+  if (dw.out_c % 32 != 0 || pw.in_c != dw.out_c || pw.out_c != pw.n_pad || pw.n_pad > 128 || pw.n_pad % 32 != 0) return false;
+  if (pw.in_c > 256) return false;  // one main accumulator: keep the accumulation chain short
+  {  // the fused kernel reads the depthwise input while it writes the 1x1 output: they must not overlap
+    const unsigned long long a0 = dw.in_off, a1 = a0 + (unsigned long long)dw.in_h * dw.in_w * dw.in_c;
+    const unsigned long long b0 = pw.out_off, b1 = b0 + (unsigned long long)pw.out_h * pw.out_w * pw.out_c;
+    if (a0 < b1 && b0 < a1) return false;
+  }
+  if (!tw.layers[pw_layer_index].ready) return false;
+  FusedPlan p;
+  if (!make_plan(dw, pw, &p)) return false;
+  // worth it only when there are enough tiles to keep every SM busy
+  return (long)p.tiles_x * p.tiles_y * n >= 148;
+}
+
+int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_index, int n, const wb_layer& dw,
+                      const wb_layer& pw, const void* in, const float* dw_w, const float* dw_scale, const float* dw_offset,
+                      const float* scale, const float* offset, void* out, std::string* err) {
+  const TcLayerWeights& w = tw.layers[pw_layer_index];
+  FusedPlan p;
+  if (!make_plan(dw, pw, &p)) {
+    *err = "fused depthwise+pointwise: no shared-memory plan";
+    return 1;
+  }
+  FusedArgs g;
+  g.dw_w = dw_w;
+  g.dw_scale = dw_scale;
+  g.dw_offset = dw_offset;
+  g.scale = scale;
+  g.offset = offset;
+  g.dw_act = dw.act;
+  g.act = pw.act;
+  g.C = dw.out_c;
+  g.S = dw.stride;
+  g.pad_t = dw.pad_t;
+  g.pad_l = dw.pad_l;
+  g.OH = dw.out_h;
+  g.OW = dw.out_w;
+  g.n_img = n;
+  g.N = pw.out_c;
+  g.block_n = p.block_n;
+  g.k_blocks = (dw.out_c + 31) / 32;
+  g.n_main = p.n_main;
+  g.tiles_x = p.tiles_x;
+  g.tiles_y = p.tiles_y;
+  g.stages = p.stages;
+  g.halo_stages = p.halo_stages;
+  g.th_in = p.th_in;
+  g.tw_in = p.tw_in;
+  alignas(64) CUtensorMap map_in, map_out, map_b, map_b_lo;
+  {
+    unsigned long long dims[4] = {(unsigned long long)dw.in_c, dw.in_w, dw.in_h, (unsigned long long)n};
+    unsigned long long st[3] = {(unsigned long long)dw.in_c * 4, (unsigned long long)dw.in_w * dw.in_c * 4,
+                                (unsigned long long)dw.in_h * dw.in_w * dw.in_c * 4};
+    unsigned box[4] = {32, (unsigned)p.tw_in, (unsigned)p.th_in, 1};
+    if (!tc_encode_map(&map_in, in, 4, 4, dims, st, box, false, err)) return 1;
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)pw.out_c, pw.out_w, pw.out_h, (unsigned long long)n};
+    unsigned long long st[3] = {(unsigned long long)pw.out_c * 4, (unsigned long long)pw.out_w * pw.out_c * 4,
+                                (unsigned long long)pw.out_h * pw.out_w * pw.out_c * 4};
+    unsigned box[4] = {32, F_TW, 2, 1};
+    if (!tc_encode_map(&map_out, out, 4, 4, dims, st, box, true, err)) return 1;
+  }
+  {
+    unsigned long long dims[2] = {(unsigned long long)w.k, (unsigned long long)w.n_pad};
+    unsigned long long st[1] = {(unsigned long long)w.k * 4};
+    unsigned box[2] = {32, (unsigned)p.block_n};
+    if (!tc_encode_map(&map_b, w.w, 4, 2, dims, st, box, true, err)) return 1;
+    if (!tc_encode_map(&map_b_lo, w.w_lo, 4, 2, dims, st, box, true, err)) return 1;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_dwpw_tc_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+      return 1;
+    }
+    attr_done = true;
+  }
+  static int ctas = 0;
+  if (ctas == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("WB_PERSIST_CTAS");
+    ctas = e ? atoi(e) : sms;
+    if (ctas <= 0 || ctas > sms) ctas = sms;
+  }
+  const long tiles = (long)p.tiles_x * p.tiles_y * n;
+  k_dwpw_tc_x3<<<dim3((unsigned)std::min<long>(tiles, ctas)), 448, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
+  ++*lc.launch_counter;
+  return 0;
+}

@@ -381,9 +381,23 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
         launch_stem<T>(lc, s.d_desc, pre, n, L, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub, w,
                        sc, of, outp);
         break;
-      case WB_OP_DW:
+      case WB_OP_DW: {
+        // depthwise -> 1x1 pairs run as one tensor-core kernel when both layers are in the requested range
+        if (c->precision == 2 && li + 1 < end) {
+          const wb_layer& P = c->layers[li + 1];
+          if (P.in_off == L.out_off && fused_dwpw_supported(c->tc, (int)li + 1, L, P, n)) {
+            std::string err;
+            if (fused_launch_dwpw(lc, c->tc, (int)li + 1, n, L, P, static_cast<const void*>(in), w, sc, of,
+                                  c->tensor(P.scale_tensor), c->tensor(P.offset_tensor),
+                                  static_cast<void*>(arena + (size_t)P.out_off * n), &err))
+              return fail("layers " + std::string(L.name) + " + " + P.name + ": " + err);
+            ++li;  // the 1x1 layer is done
+            break;
+          }
+        }
         launch_dw<T>(lc, n, L, in, w, sc, of, outp);
         break;
+      }
       case WB_OP_ADD:
         launch_add<T>(lc, (size_t)n * L.out_h * L.out_w * L.out_c, in, in2, outp);
         break;

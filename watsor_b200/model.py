@@ -120,6 +120,12 @@ class Model:
             for t in (l.src, l.src2):
                 if t:
                     last_use[t] = i
+        # a depthwise layer may be fused into the following 1x1 conv (csrc/kernels_fused.cu): the fused kernel
+        # reads the depthwise INPUT while it writes the 1x1 OUTPUT, so that input must outlive the 1x1 layer
+        for i, l in enumerate(self.layers[:-1]):
+            nxt = self.layers[i + 1]
+            if l.op == OP_DW and nxt.op == OP_PW and nxt.src == l.dst and l.src:
+                last_use[l.src] = max(last_use[l.src], i + 1)
         size = {}
         for l in self.layers:
             if l.dst:
