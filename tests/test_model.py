@@ -62,6 +62,10 @@ def check_arena(m):
         for t in (l.src, l.src2):
             if t:
                 last[t] = i
+    for i, l in enumerate(m.layers[:-1]):       # liveness extension for fused pairs, as in plan_arena
+        nxt = m.layers[i + 1]
+        if l.op == 2 and nxt.op == 3 and nxt.src == l.dst and l.src:
+            last[l.src] = max(last[l.src], i + 1)
     for i, l in enumerate(m.layers):
         if l.dst:
             size = l.out_h * l.out_w * l.out_c
@@ -71,6 +75,13 @@ def check_arena(m):
             assert l.out_off % 256 == 0 and l.out_off + size <= m.arena_elems
         for t in [t for t in live if last.get(t, -1) <= i and t != l.dst]:
             del live[t]
+    # fused depthwise -> 1x1 pairs (csrc/kernels_fused.cu) read the depthwise input while writing the 1x1 output
+    from watsor_b200.model import OP_DW, OP_PW
+    for a, b in zip(m.layers, m.layers[1:]):
+        if a.op == OP_DW and b.op == OP_PW and b.src == a.dst and a.src:
+            a0, a1 = a.in_off, a.in_off + a.in_h * a.in_w * a.in_c
+            b0, b1 = b.out_off, b.out_off + b.out_h * b.out_w * b.out_c
+            assert a1 <= b0 or b1 <= a0, (a.name, b.name)
 
 
 def test_arena_planner_and_blob_round_trip():

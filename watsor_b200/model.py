@@ -166,9 +166,8 @@ class Model:
                 l.in_off = where[l.src]
             if l.src2 and l.src2 in where:
                 l.in2_off = where[l.src2]
-            for t in {l.src, l.src2}:
-                if t and t in where and last_use[t] == i:
-                    release(where[t], size[t])
+            for t in [t for t, lu in last_use.items() if lu == i and t in where]:
+                release(where[t], size[t])
         self.arena_elems = top
 
     # -------------------------------------------------------------- (de)serialise
