@@ -5,14 +5,14 @@
 // (watsor/detection/tensorflow_cpu.py:114 runs them inside sess.run).  fp32-faithful mode only (TF32X3).
 //
 // Persistent kernel, one CTA per SM, output tile = 8 x 16 pixels of one image x all N (<= 128) channels:
-//   warp 0      TMA producer: per 32-channel k-block a 4-D box {32 ch, halo_w, halo_h, 1 image} of the
+//   warp 4      TMA producer: per 32-channel k-block a 4-D box {32 ch, halo_w, halo_h, 1 image} of the
 //               depthwise INPUT (halo included; out-of-image coordinates are zero-filled by TMA = TF SAME
 //               padding) and the 1x1 weight tiles (hi, lo)
-//   warps 6..13 depthwise producers: 3x3 taps from the halo tile in shared memory (8 lanes = the 8 channel
+//   warps 8..23 depthwise producers: 3x3 taps from the halo tile in shared memory (8 lanes = the 8 channel
 //               quads of one pixel -> conflict-free 128-byte rows, the 9 tap weights live in registers),
 //               BN + ReLU6, TF32 hi/lo split, written straight into the 128B-swizzled UMMA A tiles
-//   warp 1      tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
-//   warps 2..5  epilogue: tcgen05.ld -> BN + ReLU6 -> swizzled staging -> 4-D TMA store {32 ch, 16, 2, 1}
+//   warp 5      tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
+//   warps 0..3  epilogue: tcgen05.ld -> BN + ReLU6 -> swizzled staging -> 4-D TMA store {32 ch, 16, 2, 1}
 // The depthwise accumulation order (ky, kx) and the GEMM's k order are those of the unfused kernels, so
 // the result is bit-identical to running k_dw_strip followed by k_gemm_tc_persist.
 #include <algorithm>
@@ -56,7 +56,24 @@ struct FusedArgs {
   int th_in, tw_in;
 };
 
-__global__ void __launch_bounds__(448, 1)
+// Warp roles are laid out by warpgroup so that `setmaxnreg` can move registers from the many light
+// depthwise-producer warps to the four epilogue warps:
+//   warps 0..3   epilogue (TMEM lane quarter = warp)
+//   warp  4      TMA producer, warp 5 MMA issuer, 6..7 idle
+//   warps 8..15  depthwise producers (4 pixels x 1 channel quad per thread and k-block)
+// (16 producer warps with setmaxnreg 64/152 were measured too: not faster, the producers are bound by
+// instruction count, not by latency hiding)
+constexpr int F_PRODUCER_WARPS = 8;
+constexpr int F_FIRST_PRODUCER_THREAD = 256;
+constexpr int F_THREADS = F_FIRST_PRODUCER_THREAD + 32 * F_PRODUCER_WARPS;  // 768
+
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <int S>
+__global__ void __launch_bounds__(F_THREADS, 1)
     k_dwpw_tc_x3(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out, FusedArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,6 +92,7 @@ __global__ void __launch_bounds__(448, 1)
   uint64_t* acc_full = empty + g.stages;  // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_dw = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15 & ~(uintptr_t)15);  // [11][C]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
@@ -84,14 +102,14 @@ __global__ void __launch_bounds__(448, 1)
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * set_cols) tmem_cols <<= 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     for (int h = 0; h < g.halo_stages; ++h) {
       mbar_init(smem_u32(&halo_full[h]), 1);
-      mbar_init(smem_u32(&halo_empty[h]), 8);  // one arrive per depthwise producer warp
+      mbar_init(smem_u32(&halo_empty[h]), F_PRODUCER_WARPS);  // one arrive per depthwise producer warp
     }
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&a_ready[s]), 8);
+      mbar_init(smem_u32(&a_ready[s]), F_PRODUCER_WARPS);
       mbar_init(smem_u32(&empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -100,13 +118,24 @@ __global__ void __launch_bounds__(448, 1)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  // depthwise taps + folded BN of every channel: loaded once per CTA, read by the producers every k-block
+  for (int i = threadIdx.x; i < 9 * g.C; i += blockDim.x) s_dw[i] = g.dw_w[i];
+  for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+    s_dw[9 * g.C + i] = g.dw_scale[i];
+    s_dw[10 * g.C + i] = g.dw_offset[i];
+  }
+  float* s_pw = s_dw + 11 * g.C;  // [2][block_n]: folded BN of the pointwise output channels
+  for (int i = threadIdx.x; i < g.block_n; i += blockDim.x) {
+    s_pw[i] = g.scale[i];
+    s_pw[g.block_n + i] = g.offset[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;
@@ -118,8 +147,8 @@ __global__ void __launch_bounds__(448, 1)
           mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
           const uint32_t hb = smem_u32(&halo_full[h]);
           mbar_expect_tx(hb, (uint32_t)(g.th_in * g.tw_in * ROW_BYTES));
-          tma_load_4d(smem_u32(halo0 + (size_t)h * halo_bytes), &map_in, hb, kb * 32, ox0 * g.S - g.pad_l,
-                      oy0 * g.S - g.pad_t, img);
+          tma_load_4d(smem_u32(halo0 + (size_t)h * halo_bytes), &map_in, hb, kb * 32, ox0 * S - g.pad_l,
+                      oy0 * S - g.pad_t, img);
           mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
           const uint32_t bb = smem_u32(&b_full[s]);
           uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;
@@ -129,7 +158,7 @@ __global__ void __launch_bounds__(448, 1)
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(true, BLOCK_M, g.block_n);
     int it = 0, j = 0;
@@ -164,7 +193,7 @@ __global__ void __launch_bounds__(448, 1)
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
     uint8_t* my_stage = staging + (size_t)q * 2 * 4096;
@@ -184,17 +213,22 @@ __global__ void __launch_bounds__(448, 1)
           uint32_t v[16];
           load_acc16<true>(acc0 + (uint32_t)(c0 + hh * 16), g.block_n, g.n_main, used, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int nn = c0 + hh * 16 + i;
-            float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
-            y[hh * 16 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int nn = c0 + hh * 16 + i4 * 4;
+            const float4 sc = lds128(smem_u32(s_pw + nn)), of = lds128(smem_u32(s_pw + g.block_n + nn));
+            const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, ofs[4] = {of.x, of.y, of.z, of.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = affine_rn(__uint_as_float(v[i4 * 4 + e]), scs[e], ofs[e]);
+              y[hh * 16 + i4 * 4 + e] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+            }
           }
         }
         if (chunk_no >= 2) {
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
-        uint8_t* sb = my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128;
+        const uint32_t sb = smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 pk;
@@ -202,7 +236,7 @@ __global__ void __launch_bounds__(448, 1)
           pk.y = __float_as_uint(y[c * 4 + 1]);
           pk.z = __float_as_uint(y[c * 4 + 2]);
           pk.w = __float_as_uint(y[c * 4 + 3]);
-          *reinterpret_cast<uint4*>(sb + ((c ^ (lane & 7)) << 4)) = pk;
+          sts128(sb + (uint32_t)((c ^ (lane & 7)) << 4), pk);
         }
         fence_proxy_async();
         __syncwarp();
@@ -217,10 +251,10 @@ __global__ void __launch_bounds__(448, 1)
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
     }
     if (lane == 0) bulk_wait_read<0>();
-  } else {
-    // ------------------------------------------------------------------ depthwise producers (8 warps)
-    const int pt = threadIdx.x - 192;      // 0..255
-    const int q = pt & 7, slot = pt >> 3;  // channel quad of the k-block, pixel slot 0..31
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ depthwise producers
+    const int pt = threadIdx.x - F_FIRST_PRODUCER_THREAD;
+    const int q = pt & 7, slot = pt >> 3;  // channel quad of the k-block, pixel slot
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
@@ -228,33 +262,46 @@ __global__ void __launch_bounds__(448, 1)
         const int cch = kb * 32 + q * 4;
         float4 wr[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(g.dw_w + (size_t)k * g.C + cch));
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.dw_scale + cch));
-        const float4 of = __ldg(reinterpret_cast<const float4*>(g.dw_offset + cch));
+        for (int k = 0; k < 9; ++k) wr[k] = lds128(smem_u32(s_dw + k * g.C + cch));
+        const float4 sc = lds128(smem_u32(s_dw + 9 * g.C + cch));
+        const float4 of = lds128(smem_u32(s_dw + 10 * g.C + cch));
         mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
         mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
-        const float* hal = reinterpret_cast<const float*>(halo0 + (size_t)h * halo_bytes);
-        uint8_t* a_hi = ab0 + (size_t)s * ab_bytes;
-        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
+        const uint32_t a_hi = smem_u32(ab0 + (size_t)s * ab_bytes);
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        // One thread = 4 horizontally adjacent output pixels of one channel quad: a 3 x 6 input window is read
+        // once (18 LDS.128 instead of 36) and every input feeds up to three outputs.  Per output the taps
+        // still accumulate in (ky, kx) order, so the result is bit-identical to the stand-alone depthwise kernel.
+        static_assert(S == 1 && F_PRODUCER_WARPS == 8 && F_TW == 16 && F_TH == 8, "producer mapping");
+        constexpr int TW_IN = F_TW + 2;
+        const int ty = slot >> 2, x0 = (slot & 3) * 4;
+        const uint32_t win = hal + (uint32_t)((ty * TW_IN + x0) * 128 + q * 16);
+        float4 acc[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = slot + 32 * i;
-          const int ty = r >> 4, tx = r & 15;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const float4 x = lds128(win + (uint32_t)((ky * TW_IN + c) * 128));
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const float4 x = *reinterpret_cast<const float4*>(
-                  hal + ((size_t)((ty * g.S + ky) * g.tw_in + tx * g.S + kx) * 32 + q * 4));
-              const float4 ww = wr[ky * 3 + kx];
-              acc.x = fmaf(x.x, ww.x, acc.x);
-              acc.y = fmaf(x.y, ww.y, acc.y);
-              acc.z = fmaf(x.z, ww.z, acc.z);
-              acc.w = fmaf(x.w, ww.w, acc.w);
+              const int o = c - kx;
+              if (o >= 0 && o < 4) {
+                const float4 ww = wr[ky * 3 + kx];
+                acc[o].x = fmaf(x.x, ww.x, acc[o].x);
+                acc[o].y = fmaf(x.y, ww.y, acc[o].y);
+                acc[o].z = fmaf(x.z, ww.z, acc[o].z);
+                acc[o].w = fmaf(x.w, ww.w, acc[o].w);
+              }
             }
-          float v[4] = {affine_rn(acc.x, sc.x, of.x), affine_rn(acc.y, sc.y, of.y), affine_rn(acc.z, sc.z, of.z),
-                        affine_rn(acc.w, sc.w, of.w)};
+          }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int r = ty * F_TW + x0 + o;
+          float v[4] = {affine_rn(acc[o].x, sc.x, of.x), affine_rn(acc[o].y, sc.y, of.y),
+                        affine_rn(acc[o].z, sc.z, of.z), affine_rn(acc[o].w, sc.w, of.w)};
           uint4 hi, lo;
           uint32_t* hp = &hi.x;
           uint32_t* lp = &lo.x;
@@ -266,8 +313,8 @@ __global__ void __launch_bounds__(448, 1)
             lp[e] = __float_as_uint(__fsub_rn(a, __uint_as_float(hb))) & 0xFFFFE000u;
           }
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);  // 128B swizzle
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          sts128(a_hi + off, hi);
+          sts128(a_lo + off, lo);
         }
         fence_proxy_async();
         __syncwarp();
@@ -281,7 +328,7 @@ __global__ void __launch_bounds__(448, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -301,14 +348,14 @@ bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
   p->tiles_y = (dw.out_h + F_TH - 1) / F_TH;
   const size_t halo = ((size_t)p->th_in * p->tw_in * ROW_BYTES + 1023) / 1024 * 1024;
   const size_t ab = 2 * A_TILE_BYTES + 2 * (size_t)p->block_n * ROW_BYTES;
-  const size_t budget = 225 * 1024 - F_STAGING_BYTES;
+  const size_t budget = 224 * 1024 - F_STAGING_BYTES - 44 * (size_t)dw.out_c;
   // prefer two A/B stages, then as many halo buffers as fit (at least two)
   for (int st = 2; st >= 1; --st)
     for (int hs = 3; hs >= 2; --hs) {
       if (hs * halo + st * ab <= budget) {
         p->stages = st;
         p->halo_stages = hs;
-        p->smem = hs * halo + st * ab + F_STAGING_BYTES + 1024 + 8 * (2 * hs + 3 * st + 4) + 16;
+        p->smem = hs * halo + st * ab + F_STAGING_BYTES + 1024 + 8 * (2 * hs + 3 * st + 4) + 64 + 44 * (size_t)dw.out_c + 8 * (size_t)pw.out_c;
         return true;
       }
     }
@@ -320,7 +367,7 @@ bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
 bool fused_dwpw_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& dw, const wb_layer& pw, int n) {
   if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr) return false;
   if (dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
-  if (dw.kh != 3 || dw.kw != 3 || (dw.stride != 1 && dw.stride != 2)) return false;
+  if (dw.kh != 3 || dw.kw != 3 || dw.stride != 1) return false;  // stride 2: the 17x33 halo does not fit beside the fp32 rings
   if (dw.out_c % 32 != 0 || pw.in_c != dw.out_c || pw.out_c != pw.n_pad || pw.n_pad > 128 || pw.n_pad % 32 != 0) return false;
   if (pw.in_c > 256) return false;  // one main accumulator: keep the accumulation chain short
   {  // the fused kernel reads the depthwise input while it writes the 1x1 output: they must not overlap
@@ -393,7 +440,7 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_dwpw_tc_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dwpw_tc_x3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
       return 1;
@@ -410,7 +457,7 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
     if (ctas <= 0 || ctas > sms) ctas = sms;
   }
   const long tiles = (long)p.tiles_x * p.tiles_y * n;
-  k_dwpw_tc_x3<<<dim3((unsigned)std::min<long>(tiles, ctas)), 448, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
+  k_dwpw_tc_x3<1><<<dim3((unsigned)std::min<long>(tiles, ctas)), F_THREADS, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
   ++*lc.launch_counter;
   return 0;
 }

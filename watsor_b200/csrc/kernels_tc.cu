@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       const int s = it % g.stages;
       const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(smem_u32(&full[s]), ph);
-      uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
-      uint4* lo = a + A_TILE_BYTES / 16;
+      const uint32_t a = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t lo = a + A_TILE_BYTES;
 #pragma unroll 4
       for (int i = t; i < A_TILE_BYTES / 16; i += 128) {
-        uint4 x = a[i], h, l;
+        uint4 x = lds128u(a + i * 16), h, l;
         h.x = x.x & 0xFFFFE000u;
         h.y = x.y & 0xFFFFE000u;
         h.z = x.z & 0xFFFFE000u;
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
         l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
         l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
-        a[i] = h;
-        lo[i] = l;
+        sts128(a + i * 16, h);
+        sts128(lo + i * 16, l);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
-        uint8_t* sb = my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128;
+        const uint32_t sb = smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 pk;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
             pk.z = *reinterpret_cast<uint32_t*>(&p2);
             pk.w = *reinterpret_cast<uint32_t*>(&p3);
           }
-          *reinterpret_cast<uint4*>(sb + ((c ^ (lane & 7)) << 4)) = pk;  // 128B swizzle: chunk ^= row % 8
+          sts128(sb + (uint32_t)((c ^ (lane & 7)) << 4), pk);  // 128B swizzle: chunk ^= row % 8
         }
         fence_proxy_async();
         __syncwarp();
@@ -414,11 +414,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         const int s = it % g.stages;
         const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(smem_u32(&full[s]), ph);
-        uint4* a = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
-        uint4* lo = a + A_TILE_BYTES / 16;
+        const uint32_t a = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t lo = a + A_TILE_BYTES;
 #pragma unroll 4
         for (int i = tt; i < A_TILE_BYTES / 16; i += 128) {
-          uint4 x = a[i], h, l;
+          uint4 x = lds128u(a + i * 16), h, l;
           h.x = x.x & 0xFFFFE000u;
           h.y = x.y & 0xFFFFE000u;
           h.z = x.z & 0xFFFFE000u;
@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
           l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
           l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
-          a[i] = h;
-          lo[i] = l;
+          sts128(a + i * 16, h);
+          sts128(lo + i * 16, l);
         }
         fence_proxy_async();
         __syncwarp();

@@ -752,9 +752,22 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
   s.launches = 0;
   CK(cudaEventRecord(ev[0], st));
   for (int li = 0; li < nl; ++li) {
+    // a depthwise layer that the executor fuses into the following 1x1 conv is timed together with it:
+    // the pair's time is reported on the 1x1 layer, the depthwise entry reads 0
+    int last = li;
+    if (c->precision == 2 && li + 1 < nl && c->layers[li].op == WB_OP_DW &&
+        c->layers[li + 1].in_off == c->layers[li].out_off &&
+        fused_dwpw_supported(c->tc, li + 1, c->layers[li], c->layers[li + 1], n))
+      last = li + 1;
+    const int first = li;
+    if (last != li) {
+      CK(cudaEventRecord(ev[li + 1], st));  // zero-length interval for the depthwise entry
+      kinds[li] = (int)c->layers[li].op;
+      ++li;
+    }
     for (int r = 0; r < REPS; ++r) {
-      int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, li, li)
-                                 : run_layers<float>(c, s, st, n, nullptr, li, li);
+      int rc = c->precision == 1 ? run_layers<__nv_bfloat16>(c, s, st, n, nullptr, first, last)
+                                 : run_layers<float>(c, s, st, n, nullptr, first, last);
       if (rc) return rc;
     }
     CK(cudaEventRecord(ev[li + 1], st));
