@@ -134,10 +134,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WB_STAMP(9, 0);
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int img = t / tiles_per_img, r = t - img * tiles_per_img;
@@ -145,11 +146,13 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
           const int h = it % g.halo_stages, s = it % g.stages;
           mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
+          WB_STAMP(0, it);
           const uint32_t hb = smem_u32(&halo_full[h]);
           mbar_expect_tx(hb, (uint32_t)(g.th_in * g.tw_in * ROW_BYTES));
           tma_load_4d(smem_u32(halo0 + (size_t)h * halo_bytes), &map_in, hb, kb * 32, ox0 * S - g.pad_l,
                       oy0 * S - g.pad_t, img);
           mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
+          WB_STAMP(1, it);
           const uint32_t bb = smem_u32(&b_full[s]);
           uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;
           mbar_expect_tx(bb, 2 * b_tile_bytes);
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         mbar_wait(smem_u32(&a_ready[s]), ph);
         mbar_wait(smem_u32(&b_full[s]), ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
+          WB_STAMP(5, it);
           uint8_t* st = ab0 + (size_t)s * ab_bytes;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
           }
           umma_commit(smem_u32(&empty[s]));
           if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+          WB_STAMP(6, it);
         }
         __syncwarp();
       }
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
       const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
       mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) WB_STAMP(7, j);
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
       for (int c0 = 0; c0 < g.block_n; c0 += 32, ++chunk_no) {
         float y[32];
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           // rows q*32 .. q*32+31 of the tile = spatial rows 2q, 2q+1 (16 pixels each)
           tma_store_4d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), c0, ox0, oy0 + 2 * q, img);
           bulk_commit();
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) WB_STAMP(8, j);
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
     }
     if (lane == 0) bulk_wait_read<0>();
@@ -266,7 +273,9 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         const float4 sc = lds128(smem_u32(s_dw + 9 * g.C + cch));
         const float4 of = lds128(smem_u32(s_dw + 10 * g.C + cch));
         mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
+        if (pt == 0) WB_STAMP(2, it);
         mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
+        if (pt == 0) WB_STAMP(3, it);
         const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
         const uint32_t a_hi = smem_u32(ab0 + (size_t)s * ab_bytes);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         }
         fence_proxy_async();
         __syncwarp();
+        if (pt == 0) WB_STAMP(4, it);
         if (lane == 0) {
           mbar_arrive(smem_u32(&a_ready[s]));
           mbar_arrive(smem_u32(&halo_empty[h]));
@@ -461,3 +471,9 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
   ++*lc.launch_counter;
   return 0;
 }
+
+#ifdef WB_TRACE
+extern "C" int wb_trace_read_fused(long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, wb_trace_buf, sizeof(wb_trace_buf));
+}
+#endif

@@ -80,15 +80,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WB_STAMP(7, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb0 + it;
         const int s = it % g.stages;
         const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        WB_STAMP(0, it);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t bar = smem_u32(&full[s]);
         mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
+        WB_STAMP(3, it);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
         const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * (X3 ? 2 : 1)), b_lo = b_hi + b_tile_bytes;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         }
         umma_commit(smem_u32(&empty[s]));
         if (it == nkb - 1) umma_commit(smem_u32(acc_full));
+        WB_STAMP(4, it);
       }
       __syncwarp();
     }
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int m = m0 + row;
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
+    if (threadIdx.x == 64) WB_STAMP(5, 0);
     const int f = g.is_head ? m / g.hw : 0;
     const size_t head_row = g.is_head ? (size_t)f * g.num_anchors + g.row_off + (size_t)(m - f * g.hw) * g.anchors_per_loc : 0;
     for (int c0 = 0; c0 < g.block_n; c0 += 16) {
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           }
       }
     }
+    if (threadIdx.x == 64) WB_STAMP(6, 0);
   } else if (X3) {
     // ------------------------------------------------------------------ converters (A -> hi / lo)
     const int t = threadIdx.x - 192;  // 0..127
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       const int s = it % g.stages;
       const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(smem_u32(&full[s]), ph);
+      if (t == 0) WB_STAMP(1, it);
       const uint32_t a = smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t lo = a + A_TILE_BYTES;
 #pragma unroll 4
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
+      if (t == 0) WB_STAMP(2, it);
       if (lane == 0) mbar_arrive(smem_u32(&conv[s]));
     }
   }
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / n_tiles) * BLOCK_M, n0 = (t % n_tiles) * g.block_n;
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           uint8_t* st = smem + (size_t)s * stage_bytes;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * (X3 ? 2 : 1)), b_lo = b_hi + b_tile_bytes;
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), n0 + c0, m0 + q * 32);
           bulk_commit();
         }
@@ -788,3 +796,9 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   }
   return 0;
 }
+
+#ifdef WB_TRACE
+extern "C" int wb_trace_read_gemm(long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, wb_trace_buf, sizeof(wb_trace_buf));
+}
+#endif

@@ -51,6 +51,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One elected lane of a converged warp.  Unlike `lane == 0`, ptxas knows the guarded region runs in a single
+// thread, so the tcgen05.mma operands move to uniform registers without the per-instruction
+// ELECT / R2UR.BROADCAST / BRA.U.ANY uniformisation loop (measured: ~100 -> ~30 cycles per issued MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 template <bool TF32>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   if (TF32)
@@ -126,6 +135,23 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+
+// Pipeline tracing (diagnostic builds only: make EXTRA=-DWB_TRACE; see tools/trace_pipeline.py).  CTA 0 stamps
+// clock64() per role and iteration into a per-translation-unit buffer that wb_trace_read_*() copies out.
+#ifdef WB_TRACE
+#define WB_TRACE_SLOTS 12
+#define WB_TRACE_ITERS 64
+static __device__ long long wb_trace_buf[WB_TRACE_SLOTS * WB_TRACE_ITERS];
+#define WB_STAMP(kind, it)                                                                  \
+  do {                                                                                      \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < WB_TRACE_ITERS)     \
+      wb_trace_buf[(kind) * WB_TRACE_ITERS + (it)] = clock64();                             \
+  } while (0)
+#else
+#define WB_STAMP(kind, it) \
+  do {                     \
+  } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
