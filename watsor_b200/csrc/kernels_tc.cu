@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
         l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
         l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
-        sts128(a + i * 16, h);
+        // hi stays as loaded: the tensor core truncates fp32 inputs to tf32 exactly like the mask above
         sts128(lo + i * 16, l);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y))) & 0xFFFFE000u;
           l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z))) & 0xFFFFE000u;
           l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w))) & 0xFFFFE000u;
-          sts128(a + i * 16, h);
+          // hi stays as loaded (the tensor core truncates fp32 inputs to tf32 itself)
           sts128(lo + i * 16, l);
         }
         fence_proxy_async();
