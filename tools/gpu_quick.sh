@@ -2,7 +2,7 @@
 # Quick iteration run: tensor-core tests, a short bench, the per-layer table of its JSON line.  Logs -> gpurun_out/
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_tc.py -q --timeout=300 2>&1 | tail -5 | tee gpurun_out/quick_pytest.log
-timeout 600 python bench.py --steps 400 --warmup 20 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/quick_bench.json
+timeout 600 python bench.py --steps 1000 --warmup 20 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/quick_bench.json
 python - <<'PY'
 import json
 d = json.load(open('gpurun_out/quick_bench.json'))

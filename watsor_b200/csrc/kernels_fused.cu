@@ -214,19 +214,18 @@ __global__ void __launch_bounds__(F_THREADS, 1)
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
       for (int c0 = 0; c0 < g.block_n; c0 += 32, ++chunk_no) {
         float y[32];
+        {
+          uint32_t v[32];
+          load_acc32<true>(acc0 + (uint32_t)c0, g.block_n, g.n_main, used, v);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[16];
-          load_acc16<true>(acc0 + (uint32_t)(c0 + hh * 16), g.block_n, g.n_main, used, v);
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int nn = c0 + hh * 16 + i4 * 4;
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const int nn = c0 + i4 * 4;
             const float4 sc = lds128(smem_u32(s_pw + nn)), of = lds128(smem_u32(s_pw + g.block_n + nn));
             const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, ofs[4] = {of.x, of.y, of.z, of.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float x = affine_rn(__uint_as_float(v[i4 * 4 + e]), scs[e], ofs[e]);
-              y[hh * 16 + i4 * 4 + e] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+              y[i4 * 4 + e] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
             }
           }
         }

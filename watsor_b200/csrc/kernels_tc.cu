@@ -367,14 +367,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       for (int c0 = 0; c0 < g.block_n; c0 += CW, ++chunk_no) {
         float y[CW];
 #pragma unroll
-        for (int h = 0; h < CW / 16; ++h) {
-          uint32_t v[16];
-          load_acc16<X3>(acc0 + (uint32_t)(c0 + h * 16), g.block_n, g.n_main, used, v);
+        for (int h = 0; h < CW / 32; ++h) {
+          uint32_t v[32];
+          load_acc32<X3>(acc0 + (uint32_t)(c0 + h * 32), g.block_n, g.n_main, used, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int nn = n0 + c0 + h * 16 + i;
+          for (int i = 0; i < 32; ++i) {
+            const int nn = n0 + c0 + h * 32 + i;
             float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
-            y[h * 16 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+            y[h * 32 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
           }
         }
         // staging buffer (chunk_no & 1) was last used two chunks ago: its TMA store must have read it

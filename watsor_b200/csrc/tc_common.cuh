@@ -116,6 +116,32 @@ __device__ __forceinline__ void load_acc16(uint32_t taddr, int block_n, int n_ma
   for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(uc[i])));
 }
 
+// 32 accumulator columns at once.  With a single main accumulator (or none to add) all four / two tcgen05.ld
+// go out before one wait::ld - the epilogue warps are latency bound (profiles/r01_pipeline_trace.md), and two
+// dependent ld -> wait round trips per 32 columns were a third of their time.  Same RN additions as load_acc16.
+template <bool X3>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, int block_n, int n_main, int used, uint32_t* v) {
+  if (!X3) {
+    tmem_ld16(taddr, v);
+    tmem_ld16(taddr + 16u, v + 16);
+    tmem_ld_wait();
+    return;
+  }
+  if (used > 1) {
+    load_acc16<true>(taddr, block_n, n_main, used, v);
+    load_acc16<true>(taddr + 16u, block_n, n_main, used, v + 16);
+    return;
+  }
+  uint32_t uc[32];
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16u, v + 16);
+  tmem_ld16(taddr + (uint32_t)(n_main * block_n), uc);
+  tmem_ld16(taddr + (uint32_t)(n_main * block_n) + 16u, uc + 16);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(uc[i])));
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64).
 // Rows are 128 B apart, 8-row swizzle atoms 1024 B apart (SBO).
