@@ -54,6 +54,30 @@ def test_pointwise_gemm(precision, rel_tol, K, N, hw, n):
     assert err <= rel_tol * max(1.0, np.abs(ref).max()) * (4 if precision == 1 else 1), (err, np.abs(ref).max())
 
 
+@pytest.mark.parametrize('K,N,hw,n', [(512, 512, 19, 4), (1024, 1024, 10, 8), (256, 48, 3, 1), (64, 128, 20, 3)])
+def test_tmem_staged_a_operand(monkeypatch, K, N, hw, n):
+    """Experimental WB_TMEM_A=1 path of k_gemm_tc<2, true>: the converter warps tcgen05.st the hi / lo rows into
+    tensor memory and the MMAs take A from there.  Same bar as the shared-memory path; where both use one main
+    accumulator (chains <= 32 steps) the two must agree bit for bit."""
+    m, w1, sc, of = tiny_model(K, N, hw)
+    pre = np.random.default_rng(1).standard_normal((n, hw, hw, 3)).astype(np.float32)
+    out = {}
+    for ta in (False, True):
+        if ta:
+            monkeypatch.setenv('WB_TMEM_A', '1')
+        else:
+            monkeypatch.delenv('WB_TMEM_A', raising=False)
+        with Engine(m.to_blob(), device=0, max_batch=n, precision=2) as e:
+            _, _, a = e.backbone(pre, stop_layer=0, layer_shape=(hw, hw, K))
+            _, _, out[ta] = e.backbone(pre, stop_layer=1, layer_shape=(hw, hw, N))
+    ref = a.reshape(-1, K).astype(np.float64) @ w1.astype(np.float64)
+    ref = np.clip(ref * sc.astype(np.float64) + of.astype(np.float64), 0.0, 6.0)
+    err = np.abs(out[True].reshape(-1, N) - ref).max()
+    assert err <= 3e-6 * max(1.0, np.abs(ref).max()), (err, np.abs(ref).max())
+    if K <= 256:
+        assert np.array_equal(out[True], out[False])
+
+
 def test_fused_depthwise_pointwise_equals_unfused(shapes_model):
     """k_dwpw_tc_x3 (depthwise fused into the GEMM's A-operand producer, csrc/kernels_fused.cu) against
     the two-kernel path (WB_NO_FUSE=1): same accumulation orders, so the head outputs are bit-identical."""

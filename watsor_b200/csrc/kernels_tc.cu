@@ -33,12 +33,16 @@ struct TcArgs {
   int block_n, stages, k_blocks;
   int splits, kb_per;  // split-K over blockIdx.z (partials reduced by k_splitk_reduce)
   float* partial;      // [splits][M][n_pad]
+  int ta_stages;  // > 0: A operand staged in tensor memory (k_gemm_tc<2, true>), ring of 64-column hi/lo pairs
   int n_main;  // TF32X3: the hi*hi products rotate over n_main TMEM accumulators (+1 for the corrections)
   int act, is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1, hw;
 };
 
 // MODE 0: bf16 operands; MODE 1: tf32 single product (diagnostic); MODE 2: tf32 x3 split
-template <int MODE>
+// TA (TF32X3 only, experimental, WB_TMEM_A=1): the converter warps write the hi / lo rows into tensor memory
+// (tcgen05.st) and the MMAs take A from there, so the shared-memory port carries neither the converter writes
+// nor the A operand reads.
+template <int MODE, bool TA = false>
 __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
@@ -49,13 +53,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = g.block_n * ROW_BYTES;
-  const int stage_bytes = A_TILE_BYTES * (X3 ? 2 : 1) + b_tile_bytes * (X3 ? 2 : 1);
+  static_assert(!TA || X3, "TMEM-staged A exists for the 3xTF32 mode only");
+  constexpr int A_SLOTS = TA ? 1 : (X3 ? 2 : 1);  // fp32 tile (+ lo tile when the split stays in smem)
+  const int stage_bytes = A_TILE_BYTES * A_SLOTS + b_tile_bytes * (X3 ? 2 : 1);
   uint8_t* bar_base = smem + (size_t)g.stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);          // TMA landed
   uint64_t* empty = full + g.stages;                               // MMAs done with the stage
   uint64_t* conv = empty + g.stages;                               // converters done (X3)
   uint64_t* acc_full = conv + g.stages;                            // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* ta_conv = acc_full + 2;   // [4] TA: hi/lo rows of a TMEM stage written
+  uint64_t* ta_empty = ta_conv + 4;   // [4] TA: MMAs done with a TMEM stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * g.block_n;
@@ -64,7 +72,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
   const int n_acc = X3 ? g.n_main + 1 : 1;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < g.block_n * n_acc) tmem_cols <<= 1;
+  while ((int)tmem_cols < g.block_n * n_acc + (TA ? g.ta_stages * 64 : 0)) tmem_cols <<= 1;
+  const uint32_t a_col0 = (uint32_t)(g.block_n * n_acc);  // TA: first column of the A ring
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.stages; ++s) {
@@ -72,6 +81,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       mbar_init(smem_u32(&empty[s]), 1);
       mbar_init(smem_u32(&conv[s]), 4);  // one arrive per converter warp
     }
+    if (TA)
+      for (int s = 0; s < 4; ++s) {
+        mbar_init(smem_u32(&ta_conv[s]), 4);
+        mbar_init(smem_u32(&ta_empty[s]), 1);
+      }
     mbar_init(smem_u32(acc_full), 1);
     fence_barrier_init();
   }
@@ -95,7 +109,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         const uint32_t bar = smem_u32(&full[s]);
         mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
         tma_load_2d(smem_u32(st), &map_a, bar, kb * K_PER_BLOCK, m0);
-        uint8_t* sb = st + A_TILE_BYTES * (X3 ? 2 : 1);
+        uint8_t* sb = st + A_TILE_BYTES * A_SLOTS;
         tma_load_2d(smem_u32(sb), &map_b, bar, kb * K_PER_BLOCK, n0);
         if (X3) tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bar, kb * K_PER_BLOCK, n0);
       }
@@ -106,13 +120,20 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     for (int it = 0; it < nkb; ++it) {
       const int s = it % g.stages;
       const uint32_t ph = (it / g.stages) & 1;
-      mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
+      const int ts = TA ? it % g.ta_stages : 0;
+      if (TA) {
+        mbar_wait(smem_u32(&full[s]), ph);  // B tiles (the converters waited on it too; this is the issuer's own acquire)
+        mbar_wait(smem_u32(&ta_conv[ts]), (it / g.ta_stages) & 1);
+      } else {
+        mbar_wait(smem_u32(X3 ? &conv[s] : &full[s]), ph);
+      }
       tc_fence_after();
       if (elect_one()) {
         WB_STAMP(3, it);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * (X3 ? 2 : 1)), b_lo = b_hi + b_tile_bytes;
+        const uint32_t b_hi = smem_u32(st + A_TILE_BYTES * A_SLOTS), b_lo = b_hi + b_tile_bytes;
+        const uint32_t ta_hi = tmem_base + a_col0 + (uint32_t)(ts * 64), ta_lo = ta_hi + 32u;
         // The tensor core adds into the fp32 accumulator with truncation (round toward zero), a bias
         // that grows with the length of the accumulation chain.  TF32X3 therefore rotates the dominant
         // hi*hi products over n_main accumulators and keeps the two small correction products in a
@@ -123,6 +144,13 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           const int step = it * (ROW_BYTES / UMMA_K_BYTES) + k;
           if (!X3) {
             umma<TF32>(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+          } else if (TA) {
+            const uint32_t d_main = tmem_base + (uint32_t)((step % g.n_main) * g.block_n);
+            const uint32_t d_corr = tmem_base + (uint32_t)(g.n_main * g.block_n);
+            const uint32_t kc = (uint32_t)(k * (UMMA_K_BYTES / 4));  // 8 TF32 columns per k-step
+            umma_tf32_ta(d_main, ta_hi + kc, make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
+            umma_tf32_ta(d_corr, ta_lo + kc, make_sw128_desc(b_hi + koff), idesc, step != 0);
+            umma_tf32_ta(d_corr, ta_hi + kc, make_sw128_desc(b_lo + koff), idesc, 1u);
           } else {
             const uint32_t d_main = tmem_base + (uint32_t)((step % g.n_main) * g.block_n);
             const uint32_t d_corr = tmem_base + (uint32_t)(g.n_main * g.block_n);
@@ -132,6 +160,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           }
         }
         umma_commit(smem_u32(&empty[s]));
+        if (TA) umma_commit(smem_u32(&ta_empty[ts]));
         if (it == nkb - 1) umma_commit(smem_u32(acc_full));
         WB_STAMP(4, it);
       }
@@ -204,6 +233,38 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   } else if (X3) {
     // ------------------------------------------------------------------ converters (A -> hi / lo)
     const int t = threadIdx.x - 192;  // 0..127
+    if (TA) {
+      // thread = one row of the tile: TMEM lane quarter of this warp x lane
+      const int q = warp & 3, row = q * 32 + lane;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % g.stages, ts = it % g.ta_stages;
+        mbar_wait(smem_u32(&full[s]), (it / g.stages) & 1);
+        mbar_wait(smem_u32(&ta_empty[ts]), ((it / g.ta_stages) & 1) ^ 1);
+        tc_fence_after();
+        if (t == 0) WB_STAMP(1, it);
+        const uint32_t a = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)row * 128u;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 x = lds128u(a + (uint32_t)((c ^ (row & 7)) << 4));  // 128B swizzle: chunk ^= row % 8
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = xs[e] & 0xFFFFE000u;
+            hi[c * 4 + e] = h;
+            lo[c * 4 + e] = __float_as_uint(__fsub_rn(__uint_as_float(xs[e]), __uint_as_float(h))) & 0xFFFFE000u;
+          }
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(ts * 64);
+        tmem_st32(taddr, hi);
+        tmem_st32(taddr + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (t == 0) WB_STAMP(2, it);
+        if (lane == 0) mbar_arrive(smem_u32(&ta_conv[ts]));
+      }
+    } else
     for (int it = 0; it < nkb; ++it) {
       const int s = it % g.stages;
       const uint32_t ph = (it / g.stages) & 1;
@@ -655,7 +716,8 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.hw = L.out_h * L.out_w;
   const int x3 = mode == TC_TF32X3 ? 2 : 1;
   g.n_main = 1;
-  const int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
+  g.ta_stages = 0;
+  int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
   dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
   // latency-bound shapes: split K so that about one wave of CTAs exists (deterministic two-pass reduce)
   g.splits = 1;
@@ -702,13 +764,24 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       // accumulator halves the TMEM footprint, so two such CTAs can share an SM
       if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;
     }
+    if (mode == TC_TF32X3 && getenv("WB_TMEM_A") != nullptr) {
+      // experimental: A ring in tensor memory; chains of <= 32 steps per main accumulator
+      const int steps = g.kb_per * (ROW_BYTES / UMMA_K_BYTES);
+      const int nm = steps <= 32 ? 1 : (steps <= 64 ? 2 : 3);
+      const int ta = std::min(4, (512 - (nm + 1) * g.block_n) / 64);
+      if (ta >= 2) {
+        g.n_main = nm;
+        g.ta_stages = ta;
+        stage_bytes = A_TILE_BYTES + 2 * g.block_n * ROW_BYTES;
+      }
+    }
     stages = (200 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages > g.kb_per) stages = g.kb_per;
   }
   if (stages < 1) stages = 1;
   g.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
   CUtensorMap map_a;
   if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) return 1;
   CUtensorMap map_b, map_b_lo;
@@ -759,6 +832,13 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       attr_done[1] = true;
     }
     k_gemm_tc<1><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+  } else if (g.ta_stages > 0) {
+    static bool ta_attr_done = false;
+    if (!ta_attr_done) {
+      e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      ta_attr_done = true;
+    }
+    k_gemm_tc<2, true><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
   } else {
     if (!attr_done[2]) {
       e = cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
