@@ -8,9 +8,10 @@
 //   warp 4      TMA producer: per 32-channel k-block a 4-D box {32 ch, halo_w, halo_h, 1 image} of the
 //               depthwise INPUT (halo included; out-of-image coordinates are zero-filled by TMA = TF SAME
 //               padding) and the 1x1 weight tiles (hi, lo)
-//   warps 8..23 depthwise producers: 3x3 taps from the halo tile in shared memory (8 lanes = the 8 channel
-//               quads of one pixel -> conflict-free 128-byte rows, the 9 tap weights live in registers),
-//               BN + ReLU6, TF32 hi/lo split, written straight into the 128B-swizzled UMMA A tiles
+//   warps 8..15 depthwise producers: thread = 4 adjacent pixels x 4 channels; a 3 x 6 window of the halo tile is
+//               read once from shared memory (8 lanes = the 8 channel quads of one pixel -> conflict-free
+//               128-byte rows, the 9 tap weights live in registers), BN + ReLU6, TF32 hi/lo split, written
+//               straight into the 128B-swizzled UMMA A tiles
 //   warp 5      tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
 //   warps 0..3  epilogue: tcgen05.ld -> BN + ReLU6 -> swizzled staging -> 4-D TMA store {32 ch, 16, 2, 1}
 // The depthwise accumulation order (ky, kx) and the GEMM's k order are those of the unfused kernels, so
@@ -56,21 +57,15 @@ struct FusedArgs {
   int th_in, tw_in;
 };
 
-// Warp roles are laid out by warpgroup so that `setmaxnreg` can move registers from the many light
-// depthwise-producer warps to the four epilogue warps:
-//   warps 0..3   epilogue (TMEM lane quarter = warp)
-//   warp  4      TMA producer, warp 5 MMA issuer, 6..7 idle
+// Warp roles, by warpgroup (the epilogue warps must be warps 0..3 of a warpgroup: TMEM lane quarter = warp % 4):
+//   warps 0..3   epilogue
+//   warp  4      TMA producer, warp 5 MMA issuer, 6..7 idle (they wait at the final barrier)
 //   warps 8..15  depthwise producers (4 pixels x 1 channel quad per thread and k-block)
-// (16 producer warps with setmaxnreg 64/152 were measured too: not faster, the producers are bound by
-// instruction count, not by latency hiding)
+// 16 producer warps with `setmaxnreg` 64/152 were measured too: slower (profiles/r01_pipeline_trace.md: the
+// long pole per tile is the epilogue / the MMAs, not the depthwise arithmetic).
 constexpr int F_PRODUCER_WARPS = 8;
 constexpr int F_FIRST_PRODUCER_THREAD = 256;
-constexpr int F_THREADS = F_FIRST_PRODUCER_THREAD + 32 * F_PRODUCER_WARPS;  // 768
-
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int F_THREADS = F_FIRST_PRODUCER_THREAD + 32 * F_PRODUCER_WARPS;  // 512
 
 template <int S>
 __global__ void __launch_bounds__(F_THREADS, 1)
