@@ -154,6 +154,27 @@ int wb_filter_rows(wb_ctx* ctx, int cam_id, int n_rows, wb_detection* rows, uint
 /* anchors as the library generated them: float32 [anchors][4] (ymin,xmin,ymax,xmax) */
 int wb_anchors(wb_ctx* ctx, float* out);
 
+/* ---- host side of the filter stage (no GPU involved) ---------------------------------------------- */
+/* TrackFilter's centroid tracker, watsor/filter/track.py:19-23 (sensitivity, history) and :29-149.
+ * One tracker per camera, like the reference's one TrackFilter per camera (main.py:293-299). */
+typedef struct wb_tracker wb_tracker;
+int wb_tracker_create(int sensitivity, int history, wb_tracker** out);
+int wb_tracker_destroy(wb_tracker* tracker);
+/* One frame: rows that passed stage 1 of track.py:26 are those with WB_V_PASS in verdicts[i] (from
+ * wb_detect / wb_filter_rows), or, when verdicts is NULL, those with label > 0 (TrackFilter without
+ * predicates).  Writes the envelopes of the objects seen >= sensitivity times to out[0..*n_out) in the
+ * reference's order and sets *suspicious_activity (track.py:39).  Returns 2 if out_cap was too small. */
+int wb_tracker_update(wb_tracker* tracker, const wb_detection* rows, int n_rows, const uint32_t* verdicts,
+                      wb_detection* out, int out_cap, int* n_out, int* suspicious_activity);
+/* DetectionSieve._incoming_frame with filters == [TrackFilter] (watsor/filter/sieve.py:21-52): the frame's
+ * rows are replaced in place by the tracker's result, the remainder is zero-filled. */
+int wb_sieve_rows(wb_tracker* tracker, wb_detection* rows, int n_rows, const uint32_t* verdicts,
+                  int* suspicious_activity);
+/* test hook: iteration order of a CPython set after adding keys[0..n) (restated in tracker.cpp) */
+int wb_debug_pyset_order(const int32_t* keys, int n, int32_t* out, int* n_out);
+/* test hook: iteration order of set(range(n)).difference({i : used[i] != 0}) (track.py:90,98) */
+int wb_debug_unused_order(int n, const uint8_t* used, int32_t* out, int* n_out);
+
 /* ---- introspection used by bench.py ------------------------------------------------------------ */
 /* number of kernel launches the last wb_detect/wb_submit issued, and per-layer device time of the
  * last profiled run (wb_profile_layers runs the program once with events around every launch) */

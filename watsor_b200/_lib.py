@@ -63,6 +63,12 @@ def load():
         'wb_last_launch_count': (c_int, [c_void_p, P(c_int)]),
         'wb_profile_layers': (c_int, [c_void_p, c_int, P(c_void_p), P(c_int32), P(c_float),
                                       P(c_int32), c_int, P(c_int)]),
+        'wb_tracker_create': (c_int, [c_int, c_int, P(c_void_p)]),
+        'wb_tracker_destroy': (c_int, [c_void_p]),
+        'wb_tracker_update': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_int), P(c_int)]),
+        'wb_sieve_rows': (c_int, [c_void_p, c_void_p, c_int, c_void_p, P(c_int)]),
+        'wb_debug_pyset_order': (c_int, [P(c_int32), c_int, P(c_int32), P(c_int)]),
+        'wb_debug_unused_order': (c_int, [c_int, c_void_p, P(c_int32), P(c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
@@ -77,7 +83,9 @@ def load():
 EXPORTS = ['wb_abi_version', 'wb_last_error', 'wb_device_count', 'wb_create', 'wb_destroy',
            'wb_device_name', 'wb_set_stream', 'wb_model_info', 'wb_set_camera', 'wb_register_host',
            'wb_unregister_host', 'wb_detect', 'wb_submit', 'wb_collect', 'wb_stream_fence', 'wb_preprocess', 'wb_backbone',
-           'wb_postprocess', 'wb_filter_rows', 'wb_anchors', 'wb_last_launch_count', 'wb_profile_layers']
+           'wb_postprocess', 'wb_filter_rows', 'wb_anchors', 'wb_last_launch_count', 'wb_profile_layers',
+           'wb_tracker_create', 'wb_tracker_destroy', 'wb_tracker_update', 'wb_sieve_rows', 'wb_debug_pyset_order',
+           'wb_debug_unused_order']
 
 
 def check(rc):

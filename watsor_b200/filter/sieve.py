@@ -9,7 +9,11 @@ from ..stream.share import Detection
 
 def sieve_frame(detections, filters):
     """detections: the frame's `Detection * 100` array (modified in place).  Returns the OR of the
-    filters' suspicious-activity flags."""
+    filters' suspicious-activity flags.  The standard chain `[TrackFilter([...])]` (main.py:293-299) of this
+    package's filters takes the native route: one CUDA call for the predicates, one C++ call for tracker +
+    write-back (`TrackFilter.sieve`)."""
+    if len(filters) == 1 and getattr(filters[0], 'can_sieve', False):
+        return filters[0].sieve(detections)
     cloned = []
     for d in detections:
         c = Detection()

@@ -10,12 +10,14 @@ after the fused ones).
 Stage 2 (track.py:29-149): the centroid tracker -- per label, match each known object (newest
 first by nearest centroid), append to its history (deque, `history` long), drop unmatched objects,
 start new ones, and report objects seen at least `sensitivity` times as the envelope of their
-history.  Sequential, tiny and stateful: it stays on the host.
+history.  Sequential, tiny and stateful: it runs on the host, in C++ (`csrc/tracker.cpp`,
+`wb_tracker_update`), which also pins down what the reference leaves to its
+runtime (argsort ties, the iteration order of Python sets -- see the header of tracker.cpp).
+`sieve()` is the whole DetectionSieve body for the standard chain `[TrackFilter([...])]`
+(main.py:293-299) in two calls: `wb_filter_rows` (CUDA) + `wb_sieve_rows` (host).
 """
 import ctypes
-from collections import OrderedDict, deque
-
-import numpy as np
+from ctypes import byref, c_int, c_uint32, c_void_p
 
 from .. import _lib
 from ..stream.share import MAX_DETECTIONS, Detection
@@ -25,14 +27,15 @@ from .confidence import ConfidenceFilter
 from .mask import MaskFilter
 
 
+def _ok(rc, what):
+    if rc != 0:
+        raise _lib.WatsorB200Error('%s failed (status %d)' % (what, rc))
+
+
 def _clone(detection):
     c = Detection()
     ctypes.memmove(ctypes.addressof(c), ctypes.addressof(detection), ctypes.sizeof(Detection))
     return c
-
-
-def _centroid(bb):
-    return int((bb.x_min + bb.x_max) / 2.0), int((bb.y_min + bb.y_max) / 2.0)
 
 
 class TrackFilter(object):
@@ -40,8 +43,9 @@ class TrackFilter(object):
         self.sensitivity = sensitivity
         self.history = history
         self.filters = [] if filters is None else list(filters)
-        self.objects = OrderedDict()                    # label -> list of deque(history)
         self._slot = None
+        self._tracker = c_void_p()
+        _ok(_lib.load().wb_tracker_create(sensitivity, history, byref(self._tracker)), 'wb_tracker_create')
         self._fused, self._foreign = self._merge_tables(self.filters)
 
     # ------------------------------------------------------------------ stage 1
@@ -73,13 +77,16 @@ class TrackFilter(object):
         return {'rows': rows, 'rasters': mask.zone_rasters if mask is not None else None,
                 'width': geom.width, 'height': geom.height}, foreign
 
-    def _passing(self, detections):
-        if self._fused is None:
-            return [d for d in detections if d.label > 0 and all(f(d) for f in self.filters)]
+    def _ensure_slot(self):
         if self._slot is None:
             self._slot = alloc_slot()
             filter_engine().set_camera(self._slot, self._fused['width'], self._fused['height'],
                                        self._fused['rasters'], self._fused['rows'])
+
+    def _passing(self, detections):
+        if self._fused is None:
+            return [d for d in detections if d.label > 0 and all(f(d) for f in self.filters)]
+        self._ensure_slot()
         dets = list(detections)
         kept = []
         for base in range(0, len(dets), MAX_DETECTIONS):
@@ -98,60 +105,51 @@ class TrackFilter(object):
     def __call__(self, detections):
         return self._group_and_update(self._passing(detections))
 
+    def sieve(self, rows):
+        """DetectionSieve._incoming_frame for filters == [self] (sieve.py:21-52): `rows` (Detection * n,
+        the frame's header rows) are judged, tracked and rewritten in place.  Only available when every
+        predicate is one of this package's (no foreign callables)."""
+        assert self.can_sieve
+        n = len(rows)
+        verdicts = None
+        if self._fused is not None:
+            self._ensure_slot()
+            verdicts = (c_uint32 * n)()
+            for base in range(0, n, MAX_DETECTIONS):
+                m = min(MAX_DETECTIONS, n - base)
+                chunk = (Detection * m).from_address(ctypes.addressof(rows) + base * ctypes.sizeof(Detection))
+                v = filter_engine().filter_rows(self._slot, chunk, m)
+                for i in range(m):
+                    verdicts[base + i] = v[i]
+        sa = c_int()
+        _ok(_lib.load().wb_sieve_rows(self._tracker, rows, n, verdicts, byref(sa)), 'wb_sieve_rows')
+        return bool(sa.value)
+
+    @property
+    def can_sieve(self):
+        return not self._foreign
+
     def __del__(self):
         try:
             free_slot(self._slot)
         except Exception:
             pass
+        try:
+            if self._tracker:
+                _lib.load().wb_tracker_destroy(self._tracker)
+                self._tracker = c_void_p()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ stage 2
     def _group_and_update(self, detections):
-        groups = OrderedDict()
-        for d in detections:
-            groups.setdefault(d.label, []).append(d)
-        suspicious_activity = len(groups) > 0
-        for label in [l for l in self.objects if l not in groups]:
-            del self.objects[label]
-        for label, dets in groups.items():
-            known = self.objects.setdefault(label, [])
-            new_c = np.array([_centroid(d.bounding_box) for d in dets], dtype=np.int64).reshape(-1, 2)
-            old_c = np.array([_centroid(h[0].bounding_box) for h in known], dtype=np.int64).reshape(-1, 2)
-            used_rows, used_cols = set(), set()
-            if len(known) and len(dets):
-                diff = old_c[:, None, :].astype(np.float64) - new_c[None, :, :].astype(np.float64)
-                dist = np.sqrt((diff ** 2).sum(-1))
-                rows = np.argsort(dist.min(axis=1))
-                cols = dist.argmin(axis=1)[rows]
-                for r, c in zip(rows, cols):
-                    if r in used_rows or c in used_cols:
-                        continue
-                    known[r].append(dets[c])
-                    used_rows.add(int(r))
-                    used_cols.add(int(c))
-            for r in sorted(set(range(len(old_c))) - used_rows, reverse=True):
-                del known[r]
-            for c in sorted(set(range(len(dets))) - used_cols):
-                known.append(deque([dets[c]], maxlen=self.history))
-        result = []
-        for label, known in self.objects.items():
-            for h in known:
-                if len(h) >= self.sensitivity:
-                    result.append(self._combine(h))
-        return result, suspicious_activity
-
-    @staticmethod
-    def _combine(h):
-        out = _clone(h[0])
-        for d in list(h)[1:]:
-            out.confidence = max(out.confidence, d.confidence)
-            out.bounding_box.x_min = min(out.bounding_box.x_min, d.bounding_box.x_min)
-            out.bounding_box.y_min = min(out.bounding_box.y_min, d.bounding_box.y_min)
-            out.bounding_box.x_max = max(out.bounding_box.x_max, d.bounding_box.x_max)
-            out.bounding_box.y_max = max(out.bounding_box.y_max, d.bounding_box.y_max)
-        zones = set()
-        for d in h:
-            zones.update(z for z in d.zones if z > 0)
-        it = iter(zones)
-        for i in range(len(out.zones)):
-            out.zones[i] = next(it, 0)
-        return out
+        dets = list(detections)
+        n = len(dets)
+        rows = (Detection * max(n, 1))()
+        for i, d in enumerate(dets):
+            ctypes.memmove(ctypes.addressof(rows[i]), ctypes.addressof(d), ctypes.sizeof(Detection))
+        out = (Detection * max(n, 1))()
+        n_out, sa = c_int(), c_int()
+        _ok(_lib.load().wb_tracker_update(self._tracker, rows, n, None, out, n, byref(n_out), byref(sa)),
+            'wb_tracker_update')
+        return [_clone(out[i]) for i in range(n_out.value)], bool(sa.value)
