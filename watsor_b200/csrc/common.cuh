@@ -79,6 +79,20 @@ __device__ __forceinline__ float affine_rn(float acc, float s, float o) {
 }
 
 // ---- launchers implemented in the .cu files -------------------------------------------------------
+// cudaFuncSetAttribute applies to the current device only: "already done" is remembered per device, so that
+// several contexts on different GPUs can live in one process (the reference runs one process per detector,
+// detector.py:12-55, but nothing in the C-ABI forbids the other arrangement).
+struct PerDeviceFlag {
+  bool done[64] = {};
+  static int dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool get() const { return done[dev()]; }
+  void set() { done[dev()] = true; }
+};
+
 struct LaunchCtx {
   cudaStream_t stream;
   int* launch_counter;  // host-side counter of kernel launches (bench: gpu_launches)

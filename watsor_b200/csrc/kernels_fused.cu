@@ -442,14 +442,14 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
     if (!tc_encode_map(&map_b, w.w, 4, 2, dims, st, box, true, err)) return 1;
     if (!tc_encode_map(&map_b_lo, w.w_lo, 4, 2, dims, st, box, true, err)) return 1;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr_done;
+  if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(k_dwpw_tc_x3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
       return 1;
     }
-    attr_done = true;
+    attr_done.set();
   }
   static int ctas = 0;
   if (ctas == 0) {

@@ -517,12 +517,12 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
   // sel holds keys [n][C][max_per_class] followed by anchor indices (int) of the same shape
   unsigned long long* sel_key = sel;
   int* sel_idx = reinterpret_cast<int*>(sel + (size_t)n * C * pp.max_per_class);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr_done;
+  if (!attr_done.get()) {
     cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
     cudaFuncSetAttribute(k_decode_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
+    attr_done.set();
   }
   k_nms<<<dim3(C, n), 256, 2 * sizeof(unsigned long long) * sort_cap, lc.stream>>>(
       pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx);

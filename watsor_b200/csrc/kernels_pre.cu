@@ -284,10 +284,10 @@ void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre,
     ++*lc.launch_counter;
     return;
   }
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
+  static PerDeviceFlag attr_done;
+  if (!attr_done.get() && smem > 48 * 1024) {
     cudaFuncSetAttribute(k_stem<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+    attr_done.set();
   }
   k_stem<T><<<grid, ST_TY * ST_TX, smem, lc.stream>>>(frames, pre, L, in_h, in_w, mul, sub, w, scale, offset, out);
   ++*lc.launch_counter;

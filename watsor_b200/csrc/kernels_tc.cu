@@ -796,7 +796,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       map_b_lo = map_b;
     }
   }
-  static bool attr_done[6] = {false, false, false, false, false, false};
+  static PerDeviceFlag attr_done[6];
   cudaError_t e = cudaSuccess;
   if (persist) {
     CUtensorMap map_out;
@@ -810,39 +810,39 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     }
     dim3 pgrid((unsigned)std::min<long>(tiles, persist_ctas));
     if (mode == TC_BF16) {
-      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (!attr_done[idx].get()) e = cudaFuncSetAttribute(k_gemm_tc_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       k_gemm_tc_persist<0><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
     } else if (mode == TC_TF32X1) {
-      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (!attr_done[idx].get()) e = cudaFuncSetAttribute(k_gemm_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       k_gemm_tc_persist<1><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
     } else {
-      if (!attr_done[idx]) e = cudaFuncSetAttribute(k_gemm_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (!attr_done[idx].get()) e = cudaFuncSetAttribute(k_gemm_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       k_gemm_tc_persist<2><<<pgrid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
     }
-    attr_done[idx] = true;
+    attr_done[idx].set();
   } else if (mode == TC_BF16) {
-    if (!attr_done[0]) {
+    if (!attr_done[0].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      attr_done[0] = true;
+      attr_done[0].set();
     }
     k_gemm_tc<0><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
   } else if (mode == TC_TF32X1) {
-    if (!attr_done[1]) {
+    if (!attr_done[1].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      attr_done[1] = true;
+      attr_done[1].set();
     }
     k_gemm_tc<1><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
   } else if (g.ta_stages > 0) {
-    static bool ta_attr_done = false;
-    if (!ta_attr_done) {
+    static PerDeviceFlag ta_attr_done;
+    if (!ta_attr_done.get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      ta_attr_done = true;
+      ta_attr_done.set();
     }
     k_gemm_tc<2, true><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
   } else {
-    if (!attr_done[2]) {
+    if (!attr_done[2].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      attr_done[2] = true;
+      attr_done[2].set();
     }
     k_gemm_tc<2><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
   }
