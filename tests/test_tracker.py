@@ -253,3 +253,47 @@ def test_sieve_rows_with_verdicts_equals_oracle_chain(seed):
         assert got[:len(want)] == [d.key() for d in want], frame
         assert all(g == (0, (0,) * 10, 0.0, 0, 0, 0, 0) for g in got[len(want):])
     lib.wb_tracker_destroy(h)
+
+
+def test_tracker_edge_cases():
+    lib = _lib.load()
+    # sensitivity above history: objects are tracked but never reported (track.py:108-110)
+    t = NativeTracker(sensitivity=3, history=2)
+    for _ in range(5):
+        out, sa = t([mk(1, 0.9, (10, 10, 20, 20))])
+        assert sa and out == []
+    # a label that disappears loses its history and starts over (track.py:41-46)
+    t = NativeTracker(sensitivity=2, history=5)
+    assert t([mk(1, 0.9, (10, 10, 20, 20))])[0] == []
+    assert len(t([mk(1, 0.8, (11, 11, 21, 21))])[0]) == 1
+    assert t([mk(2, 0.9, (10, 10, 20, 20))])[0] == []                 # label 1 gone, label 2 new
+    assert t([mk(1, 0.9, (10, 10, 20, 20)), mk(2, 0.7, (12, 12, 22, 22))])[0][0].label == 2
+    # history window: the envelope forgets boxes older than `history` frames (deque maxlen)
+    t = NativeTracker(sensitivity=1, history=2)
+    t([mk(1, 0.9, (0, 0, 10, 10))])
+    t([mk(1, 0.5, (2, 2, 12, 12))])
+    out, _ = t([mk(1, 0.6, (4, 4, 14, 14))])
+    assert key(out[0])[2:] == (0.6, 2, 2, 14, 14)                    # first frame dropped, max conf of the last two
+    # empty input, bad arguments, out_cap too small
+    h = ctypes.c_void_p()
+    assert lib.wb_tracker_create(1, 0, ctypes.byref(h)) != 0          # deque(maxlen=0) cannot hold a detection
+    assert lib.wb_tracker_create(1, 3, ctypes.byref(h)) == 0
+    n_out, sa = ctypes.c_int(-1), ctypes.c_int(-1)
+    assert lib.wb_tracker_update(h, None, 0, None, None, 0, ctypes.byref(n_out), ctypes.byref(sa)) == 0
+    assert (n_out.value, sa.value) == (0, 0)
+    rows = (Detection * 3)()
+    for i in range(3):
+        rows[i].label, rows[i].bounding_box = 1, BoundingBox(50 * i, 0, 50 * i + 10, 10)
+    out = (Detection * 1)()
+    assert lib.wb_tracker_update(h, rows, 3, None, out, 1, ctypes.byref(n_out), ctypes.byref(sa)) == 2
+    assert n_out.value == 3 and out[0].bounding_box.x_min == 0
+    assert lib.wb_tracker_update(h, rows, -1, None, out, 1, ctypes.byref(n_out), ctypes.byref(sa)) == 1
+    lib.wb_tracker_destroy(h)
+
+
+def test_negative_and_unordered_boxes_use_python_int_truncation():
+    # track.py:120-123: int((a + b) / 2.0) truncates toward zero, also for negative sums
+    t = NativeTracker(sensitivity=1, history=3)
+    t([mk(1, 0.9, (-7, -7, 0, 0)), mk(1, 0.9, (-3, -3, 0, 0))])       # centroids (-3,-3) and (-1,-1)
+    out, _ = t([mk(1, 0.8, (-4, -4, 0, 0))])                          # centroid (-2,-2): equidistant -> lower row first
+    assert key(out[0])[3:] == (-7, -7, 0, 0) and len(out) == 1
