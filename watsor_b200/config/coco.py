@@ -20,7 +20,8 @@ CocoClass = namedtuple('CocoClass', ['index', 'label'])
 
 
 def get_coco_class(idx):
-    """Label record for an index; unknown indices map to 'unlabeled' (coco.py:124-131)."""
+    """Label record for an index; unknown indices map to 'unlabeled' (coco.py:124-131).  The reference's record
+    also carries drawing attributes (box / font colours) for its output stage, which is out of scope here."""
     if 0 <= idx < len(COCO_CLASSES):
         return CocoClass(idx, COCO_CLASSES[idx])
     return CocoClass(0, COCO_CLASSES[0])
