@@ -172,6 +172,8 @@ int wb_sieve_rows(wb_tracker* tracker, wb_detection* rows, int n_rows, const uin
                   int* suspicious_activity);
 /* test hook: iteration order of a CPython set after adding keys[0..n) (restated in tracker.cpp) */
 int wb_debug_pyset_order(const int32_t* keys, int n, int32_t* out, int* n_out);
+/* test hook: np.argsort(keys) (default kind) as restated in tracker.cpp */
+int wb_debug_argsort(const int64_t* keys, int n, int32_t* out);
 /* test hook: iteration order of set(range(n)).difference({i : used[i] != 0}) (track.py:90,98) */
 int wb_debug_unused_order(int n, const uint8_t* used, int32_t* out, int* n_out);
 

@@ -297,3 +297,89 @@ def test_negative_and_unordered_boxes_use_python_int_truncation():
     t([mk(1, 0.9, (-7, -7, 0, 0)), mk(1, 0.9, (-3, -3, 0, 0))])       # centroids (-3,-3) and (-1,-1)
     out, _ = t([mk(1, 0.8, (-4, -4, 0, 0))])                          # centroid (-2,-2): equidistant -> lower row first
     assert key(out[0])[3:] == (-7, -7, 0, 0) and len(out) == 1
+
+
+_SCALAR_NUMPY_SCRIPT = r'''
+import ctypes, json, random, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+from watsor_b200 import _lib
+lib = _lib.load()
+rng = np.random.default_rng(3)
+res = {'argsort_mismatch': 0, 'argsort_cases': 0, 'unstable_seen': 0}
+for n in list(range(0, 110)) + [160, 100]:
+    for vals in (2, 3, 7, 60, 10 ** 9):
+        for _ in range(6):
+            a = rng.integers(0, vals, n).astype(np.int64)
+            want = np.argsort(a.astype(np.float64))
+            res['unstable_seen'] += int(not np.array_equal(want, np.argsort(a, kind='stable')))
+            out = (ctypes.c_int32 * max(n, 1))()
+            assert lib.wb_debug_argsort(a.ctypes.data, n, out) == 0
+            res['argsort_cases'] += 1
+            res['argsort_mismatch'] += int(list(out[:n]) != list(want))
+# organ-pipe / sawtooth patterns: deeper partition trees
+for n in (64, 100):
+    for a in (np.r_[np.arange(n // 2), np.arange(n // 2)[::-1]], np.arange(n) %% 5, np.zeros(n), np.arange(n)[::-1] // 3):
+        a = a.astype(np.int64)
+        out = (ctypes.c_int32 * n)()
+        lib.wb_debug_argsort(a.ctypes.data, n, out)
+        res['argsort_cases'] += 1
+        res['argsort_mismatch'] += int(list(out) != list(np.argsort(a.astype(np.float64))))
+res['track_diverging'] = -1
+if %(with_ref)r:
+    from tests.test_tracker import NativeTracker, mk, key
+    sys.path.insert(0, %(ref)r)
+    from watsor.filter.track import TrackFilter
+    from watsor.stream.share import BoundingBox, Detection
+    bad = 0
+    for max_n, grid in ((12, 6), (24, 20), (40, 6), (40, 60), (100, 30)):
+        for seed in range(8):
+            r = random.Random(seed)
+            nat, ref = NativeTracker(2, 4), TrackFilter(sensitivity=2, history=4)
+            for f in range(40):
+                dets = []
+                for _ in range(r.randint(0, max_n)):
+                    x, y = r.randint(0, grid), r.randint(0, grid)
+                    dets.append((r.randint(1, 2), 0.5 + 0.01 * r.randint(0, 40), (x, y, x + r.choice([2, 4]), y + r.choice([2, 4])),
+                                 [r.randint(1, 12)] if r.random() < 0.5 else []))
+                got, _ = nat([mk(*d) for d in dets])
+                rd = []
+                for l, c, b, z in dets:
+                    d = Detection(label=l, confidence=c, bounding_box=BoundingBox(*b))
+                    for i, zz in enumerate(z):
+                        d.zones[i] = zz
+                    rd.append(d)
+                exp, _ = ref(rd)
+                if [key(d) for d in got] != [key(d) for d in exp]:
+                    bad += 1
+                    break
+    res['track_diverging'] = bad
+print(json.dumps(res))
+'''
+
+
+def test_argsort_and_tie_heavy_tracking_match_numpy_scalar_sort():
+    """numpy_argsort() in tracker.cpp is numpy's index introsort; numpy >= 1.25 replaces it by SIMD sorting networks
+    on AVX2 / AVX-512 machines, so the comparison runs in a child interpreter with those code paths disabled
+    (NPY_DISABLE_CPU_FEATURES) -- the arithmetic of the reference's pinned numpy 1.23.  With it, the tie-heavy
+    tracking sequences (tiny coordinate grids, up to 100 detections of a label per frame) equal the reference's
+    TrackFilter on every frame."""
+    import json
+    import subprocess
+    from numpy._core._multiarray_umath import __cpu_features__ as feats
+    simd = [k for k, v in feats.items() if v and (k.startswith('AVX512') or k in ('AVX2', 'FMA3'))
+            and k in ('AVX2', 'FMA3', 'AVX512F', 'AVX512CD', 'AVX512_KNL', 'AVX512_KNM', 'AVX512_SKX', 'AVX512_CLX',
+                      'AVX512_CNL', 'AVX512_ICL', 'AVX512_SPR')]
+    env = dict(os.environ)
+    if simd:
+        env['NPY_DISABLE_CPU_FEATURES'] = ' '.join(simd)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _SCALAR_NUMPY_SCRIPT % {'root': root, 'ref': REF, 'with_ref': os.path.isdir(REF)}
+    p = subprocess.run([sys.executable, '-c', script], env=env, capture_output=True, text=True, timeout=300)
+    if p.returncode != 0 and 'NPY_DISABLE_CPU_FEATURES' in p.stderr:
+        pytest.skip('numpy refused to disable its SIMD dispatch: ' + p.stderr.strip().splitlines()[-1])
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res['unstable_seen'] > 0                              # the cases do exercise non-stable orders
+    assert res['argsort_mismatch'] == 0, res
+    assert res['track_diverging'] in (0, -1), res

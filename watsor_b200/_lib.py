@@ -69,6 +69,7 @@ def load():
         'wb_sieve_rows': (c_int, [c_void_p, c_void_p, c_int, c_void_p, P(c_int)]),
         'wb_debug_pyset_order': (c_int, [P(c_int32), c_int, P(c_int32), P(c_int)]),
         'wb_debug_unused_order': (c_int, [c_int, c_void_p, P(c_int32), P(c_int)]),
+        'wb_debug_argsort': (c_int, [c_void_p, c_int, P(c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
@@ -85,7 +86,7 @@ EXPORTS = ['wb_abi_version', 'wb_last_error', 'wb_device_count', 'wb_create', 'w
            'wb_unregister_host', 'wb_detect', 'wb_submit', 'wb_collect', 'wb_stream_fence', 'wb_preprocess', 'wb_backbone',
            'wb_postprocess', 'wb_filter_rows', 'wb_anchors', 'wb_last_launch_count', 'wb_profile_layers',
            'wb_tracker_create', 'wb_tracker_destroy', 'wb_tracker_update', 'wb_sieve_rows', 'wb_debug_pyset_order',
-           'wb_debug_unused_order']
+           'wb_debug_unused_order', 'wb_debug_argsort']
 
 
 def check(rc):

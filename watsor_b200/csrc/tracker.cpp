@@ -7,8 +7,13 @@
 //   * dict / defaultdict iteration = insertion order (labels), list order (objects of a label);
 //   * scipy cdist + np.amin/argmin/argsort: compared as exact integer squared distances (sqrt is monotonic and
 //     the sums are < 2^53, so order and ties are those of the float64 distances); argmin = first minimum;
-//     argsort ties -> lower index first (numpy 1.23's insertion sort for <= 16 rows, the pinned version of the
-//     reference, docker/Dockerfile.base:33; for > 16 tied rows numpy's introsort order is unspecified);
+//     argsort = numpy's default `quicksort` kind for float64, restated in numpy_argsort(): an index introsort --
+//     median-of-3 partitions down to 16 elements, insertion sort below, heapsort past the depth limit
+//     (numpy/core/src/npysort/quicksort.cpp; the reference pins numpy 1.23, docker/Dockerfile.base:33).  Up to
+//     16 rows it is a plain insertion sort, i.e. ties keep the lower index first; above that the tie order is
+//     whatever the partitions produce, and it is reproduced here step for step (checked against numpy's scalar
+//     code path in tests/test_tracker.py; numpy >= 1.25 on AVX2/AVX-512 machines sorts with SIMD networks and
+//     orders ties differently -- that is not the reference's environment);
 //   * `for col in unused_cols` and the zone union iterate CPython *sets* of small ints: slot order of the open-
 //     addressing table (Objects/setobject.c: 8 slots minimum, fill*5 >= mask*3 -> resize to > 4*used,
 //     9 linear probes, perturb shift 5), restated in PySmallIntSet and pinned against the interpreter in
@@ -93,6 +98,107 @@ class PySmallIntSet {
   std::vector<int> table_;
   size_t fill_;
 };
+
+// np.argsort(v) for float64 keys without NaNs, `kind='quicksort'` (the default): numpy's aquicksort_ / aheapsort_.
+// `v` holds exact integer squared distances; their order and ties are those of the float64 distances.
+void numpy_heapsort(const long long* v, int* tosort, int n) {
+  int* a = tosort - 1;  // 1-based
+  for (int l = n >> 1; l > 0; --l) {
+    const int tmp = a[l];
+    int i = l, j = l << 1;
+    while (j <= n) {
+      if (j < n && v[a[j]] < v[a[j + 1]]) ++j;
+      if (v[tmp] < v[a[j]]) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else {
+        break;
+      }
+    }
+    a[i] = tmp;
+  }
+  while (n > 1) {
+    const int tmp = a[n];
+    a[n] = a[1];
+    --n;
+    int i = 1, j = 2;
+    while (j <= n) {
+      if (j < n && v[a[j]] < v[a[j + 1]]) ++j;
+      if (v[tmp] < v[a[j]]) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else {
+        break;
+      }
+    }
+    a[i] = tmp;
+  }
+}
+
+void numpy_argsort(const long long* v, int num, std::vector<int>* order) {
+  constexpr int kSmall = 15;  // partitions of more than 16 elements are split, the rest is insertion-sorted
+  order->resize((size_t)num);
+  int* t = order->data();
+  for (int i = 0; i < num; ++i) t[i] = i;
+  if (num < 2) return;
+  int* pl = t;
+  int* pr = t + num - 1;
+  int* stack[128];
+  int depth[64];
+  int** sptr = stack;
+  int* psdepth = depth;
+  int msb = 0;
+  for (unsigned m = (unsigned)num >> 1; m != 0; m >>= 1) ++msb;
+  int cdepth = msb * 2;
+  while (true) {
+    if (cdepth < 0) {
+      numpy_heapsort(v, pl, (int)(pr - pl) + 1);
+    } else {
+      while (pr - pl > kSmall) {
+        int* pm = pl + ((pr - pl) >> 1);
+        if (v[*pm] < v[*pl]) std::swap(*pm, *pl);
+        if (v[*pr] < v[*pm]) std::swap(*pr, *pm);
+        if (v[*pm] < v[*pl]) std::swap(*pm, *pl);
+        const long long vp = v[*pm];
+        int* pi = pl;
+        int* pj = pr - 1;
+        std::swap(*pm, *pj);
+        for (;;) {
+          do { ++pi; } while (v[*pi] < vp);
+          do { --pj; } while (vp < v[*pj]);
+          if (pi >= pj) break;
+          std::swap(*pi, *pj);
+        }
+        int* pk = pr - 1;
+        std::swap(*pi, *pk);
+        if (pi - pl < pr - pi) {  // the larger partition waits on the stack
+          *sptr++ = pi + 1;
+          *sptr++ = pr;
+          pr = pi - 1;
+        } else {
+          *sptr++ = pl;
+          *sptr++ = pi - 1;
+          pl = pi + 1;
+        }
+        *psdepth++ = --cdepth;
+      }
+      for (int* pi = pl + 1; pi <= pr; ++pi) {  // insertion sort
+        const int vi = *pi;
+        const long long vp = v[vi];
+        int* pj = pi;
+        int* pk = pi - 1;
+        while (pj > pl && vp < v[*pk]) *pj-- = *pk--;
+        *pj = vi;
+      }
+    }
+    if (sptr == stack) break;
+    pr = *(--sptr);
+    pl = *(--sptr);
+    cdepth = *(--psdepth);
+  }
+}
 
 // Iteration order of `set(range(n)).difference(used)` (track.py:90,98).  CPython copies the left set and removes
 // when it is more than four times larger than the right one (the copy keeps the ascending slot order of
@@ -243,9 +349,7 @@ int wb_tracker_update(wb_tracker* t, const wb_detection* rows, int n_rows, const
           row_min[r] = best;
           row_arg[r] = arg;
         }
-        order.resize((size_t)n_ex);
-        for (int r = 0; r < n_ex; ++r) order[r] = r;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_min[a] < row_min[b]; });
+        numpy_argsort(row_min.data(), n_ex, &order);
         for (int r : order) {
           const int c = row_arg[r];
           if (used_r[r] || used_c[c]) continue;
@@ -312,6 +416,16 @@ int wb_debug_pyset_order(const int32_t* keys, int n, int32_t* out, int* n_out) {
   int k = 0;
   s.for_each([&](int key) { out[k++] = key; });
   *n_out = k;
+  return 0;
+}
+
+int wb_debug_argsort(const int64_t* keys, int n, int32_t* out) {
+  // np.argsort(keys) as the tracker restates it (test hook for numpy_argsort)
+  if (n < 0 || (keys == nullptr && n > 0) || (out == nullptr && n > 0)) return 1;
+  std::vector<long long> v(keys, keys + n);
+  std::vector<int> order;
+  numpy_argsort(v.data(), n, &order);
+  for (int i = 0; i < n; ++i) out[i] = order[i];
   return 0;
 }
 
