@@ -5,17 +5,24 @@
     python bench.py --impl reference --gpus N --steps K ...  CPU arm: the reference path's CPU
                                                              restatement (oracle/), all host threads
 
-A step = one tick of the hot path over one batch: one 640x480 RGB frame from each of the C cameras
-a GPU serves (default 8 = BASELINE configs[2]; 8 GPUs x 8 cameras = configs[3]'s 64 streams), i.e.
-resize+normalise -> SSD-MobileNet-v1 convs + heads -> decode -> per-class NMS -> top-100 ->
-integer conversion -> confidence/area/mask-zone predicates -> Detection[100] per frame.
+Default workload = BASELINE configs[2] to the letter (tests/workload.py): 8 cameras of 640x480 synthetic RGB
+per GPU, batched, SSD-MobileNet-v2 300x300 with 90 COCO classes at the model-zoo score threshold 1e-8 (all
+1917 anchors are NMS candidates in every class), a mask on every camera (camera 0 = the reference's porch.png,
+cameras 1..7 synthetic RGBA masks), per-class filter defaults confidence 50 / area 10.  x8 GPUs = configs[3].
+
+A step = one tick of the hot path over one batch: one frame from each of the C cameras a GPU serves, i.e.
+resize+normalise -> SSD convs + heads -> decode -> per-class NMS -> top-100 -> integer conversion ->
+confidence/area/mask-zone predicates -> Detection[100] per frame.
 
   value  device-timed throughput with frames already resident in HBM (ring of distinct frames per
-         camera, larger than L2, so every step reads its input from HBM)
+         camera, larger than L2, so every step reads its input from HBM), exactly K steps
   e2e    same metric through the public detector API with HOST frames in pinned memory:
          H2D of every frame and D2H of every Detection block inside the timed region
-Multi-GPU: one process per GPU (torchrun), cameras sharded, no data-path collective (weak scaling);
-`--ingest scatter` adds the NCCL frame scatter from rank 0 that BASELINE.json's north star names.
+  config.real_weights   the same two numbers on the only model with real weights (the reference's vendored
+         3-class SSD-MobileNet-v1, watsor/test/model/cpu.pb), porch mask on camera 0
+Multi-GPU: one process per GPU (torchrun), cameras sharded, no data-path collective (weak scaling); the
+N>1 line adds a `scatter` record: the same steps with the NCCL frame scatter from rank 0 that BASELINE.json's
+north star names.
 """
 import argparse
 import json
@@ -43,9 +50,9 @@ def parse_args():
     p.add_argument('--warmup', type=int, default=20)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--cameras', type=int, default=8, help='cameras (= batch) per GPU')
-    p.add_argument('--model', default='shapes', choices=['shapes', 'coco', 'v2'],
-                   help='shapes: vendored 3-class SSD-MobileNet-v1 (real weights); coco: same backbone, '
-                        '90-class heads, seeded synthetic weights')
+    p.add_argument('--model', default='v2', choices=['v2', 'coco', 'shapes'],
+                   help='v2: SSD-MobileNet-v2, 90 classes (BASELINE configs[2], default); coco: SSD-MobileNet-v1 '
+                        'backbone, 90-class heads; shapes: vendored 3-class SSD-MobileNet-v1 (real weights)')
     p.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'bf16'],
                    help='fp32: CUDA-core FFMA convs; tf32x3: fp32-faithful tcgen05 (3xTF32 split); bf16: tcgen05 bf16')
     p.add_argument('--frames', default='artist', choices=['artist', 'random'])
@@ -53,12 +60,18 @@ def parse_args():
     p.add_argument('--inflight', type=int, default=6, help='batches kept in flight (library slots, max 6)')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-roofline', action='store_true')
+    p.add_argument('--no-real-weights', action='store_true', help='skip the second (real-weights v1) record')
+    p.add_argument('--no-scatter', action='store_true', help='skip the NCCL scatter record at N>1')
+    p.add_argument('--no-worker', action='store_true', help='skip the e2e_worker record')
+    p.add_argument('--min-seconds', type=float, default=1.0,
+                   help='the *_long / e2e measurements run at least this long')
     return p.parse_args()
 
 
 # ------------------------------------------------------------------------------------------ inputs
 def load_model(kind):
-    from watsor_b200.model import Model, synthetic_ssd_mobilenet_v1, synthetic_ssd_mobilenet_v2
+    from watsor_b200.model import Model, synthetic_ssd_mobilenet_v1
+    from tests.workload import v2_coco_model
     blob = os.path.join(ROOT, 'models', '_ref', 'ssd_mobilenet_v1_shapes', 'b200.wb200')
     if kind == 'shapes' and os.path.isfile(blob):
         return Model.load(blob), 'ssd_mobilenet_v1 300x300, 3 classes, real weights (watsor/test/model/cpu.pb)'
@@ -66,8 +79,9 @@ def load_model(kind):
         return (synthetic_ssd_mobilenet_v1(num_classes=3, seed=1, score_thr=0.3),
                 'ssd_mobilenet_v1 300x300, 3 classes, seeded synthetic weights (vendored blob missing)')
     if kind == 'v2':
-        return (synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8),
-                'ssd_mobilenet_v2 300x300, 90-class heads, seeded synthetic weights (no v2 weights exist offline)')
+        return (v2_coco_model(),
+                'ssd_mobilenet_v2 300x300, 90 classes, score threshold 1e-8, seeded synthetic weights '
+                '(no v2 weights exist offline)')
     return (synthetic_ssd_mobilenet_v1(num_classes=90, seed=0, score_thr=1e-8),
             'ssd_mobilenet_v1 300x300, 90-class heads, seeded synthetic weights')
 
@@ -80,17 +94,29 @@ def make_frames(kind, cam, count):
     return [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(count)]
 
 
-def camera_config(cam):
-    """cam 0 of every GPU: config/porch.png (2 zones); others: synthetic masks are generated by
-    tests/test_oracle_filters.random_mask would need files, so they run confidence+area only."""
-    detect = [{'person': {'confidence': 50, 'area': 1, 'zones': []}},
-              {'bicycle': {'confidence': 50, 'area': 1, 'zones': []}},
-              {'car': {'confidence': 50, 'area': 10, 'zones': []}}]
-    cfg = {'width': W, 'height': H, 'detect': detect}
-    porch = os.path.join(ROOT, 'tests', 'golden', 'porch.png')
-    if cam == 0 and os.path.isfile(porch):
-        cfg['mask'] = porch
-    return cfg
+def camera_config(cam, model_kind):
+    """configs[2]: a mask on every camera, schema-default thresholds for every COCO label.  The 3-class
+    real-weights model keeps round 1's configuration (its labels 1..3 are person/bicycle/car ids)."""
+    from tests import workload
+    if model_kind == 'shapes':
+        detect = [{'person': {'confidence': 50, 'area': 1, 'zones': []}},
+                  {'bicycle': {'confidence': 50, 'area': 1, 'zones': []}},
+                  {'car': {'confidence': 50, 'area': 10, 'zones': []}}]
+        cfg = {'width': W, 'height': H, 'detect': detect}
+        if cam == 0 and os.path.isfile(workload.PORCH):
+            cfg['mask'] = workload.PORCH
+        return cfg
+    return workload.camera_config(cam % 8)
+
+
+def workload_name(args):
+    if args.model == 'shapes':
+        return ('%d cameras x 640x480 synthetic RGB per GPU, batched, SSD-MobileNet-v1 300x300 (3 classes, real '
+                'weights), per-camera confidence/area filters + porch.png mask zones on camera 0' % args.cameras)
+    return ('BASELINE configs[2]: %d cameras x 640x480 synthetic RGB per GPU, batched, %s 300x300, 90-class NMS at '
+            'score threshold 1e-8, a mask on every camera (cam 0 porch.png, others synthetic RGBA), per-class '
+            'defaults confidence 50 / area 10 (x8 GPUs = configs[3])'
+            % (args.cameras, 'SSD-MobileNet-v2' if args.model == 'v2' else 'SSD-MobileNet-v1'))
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -175,7 +201,7 @@ def oracle_step_fn(model, args):
 
     def filters_for(cam):
         if cam not in filt:
-            cfg = camera_config(cam)
+            cfg = camera_config(cam, args.model)
             fs = [ConfidenceOracle(cfg), AreaOracle(cfg)]
             if 'mask' in cfg:
                 fs.append(MaskOracle(cfg))
@@ -235,13 +261,188 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    return ('%d cameras x 640x480 synthetic RGB per GPU, batched, SSD-MobileNet-v1 300x300, per-camera '
-            'confidence/area filters + porch.png mask zones on camera 0 (BASELINE configs[2]; x8 GPUs = configs[3])'
-            % args.cameras)
-
-
 # --------------------------------------------------------------------------------------- our arm
+class Arm:
+    """One detector (model + camera tables) on this rank's GPU plus its input rings, and the two timed loops."""
+
+    def __init__(self, args, model_kind, rank, local_rank, world, torch, dist):
+        from watsor_b200.detection.b200 import B200ObjectDetector
+        from watsor_b200.parallel import camera_shard
+        from watsor_b200.stream.share import Detection
+        self.args, self.rank, self.world, self.torch, self.dist = args, rank, world, torch, dist
+        self.model_kind = model_kind
+        self.model, self.model_desc = load_model(model_kind)
+        self.C = C = args.cameras
+        self.precision = {'fp32': 0, 'bf16': 1, 'tf32x3': 2}[args.precision]
+        self.det = B200ObjectDetector(None, device=local_rank, max_batch=C, precision=self.precision,
+                                      model_blob=self.model.to_blob())
+        for c in range(C):
+            self.det.configure_camera(c, W, H, camera_config(c, model_kind))
+        self.cam_ids = list(range(C))
+        # input ring: distinct frames per camera, total > L2, so each step's input comes from HBM
+        self.frame_bytes = W * H * 3
+        self.ring = ring = max(4, -(-int(1.4 * L2_BYTES) // (C * self.frame_bytes)))
+        self.base = [make_frames(args.frames, g, min(ring, 6)) for g in camera_shard(rank, world, C)]
+        self.host_ring = torch.empty((ring, C, H, W, 3), dtype=torch.uint8).pin_memory()
+        rng = np.random.default_rng(1234 + rank)
+        for r in range(ring):
+            for c in range(C):
+                img = self.base[c][r % len(self.base[c])]
+                if r >= len(self.base[c]):          # distinct bytes per ring slot: roll the picture a little
+                    img = np.roll(img, shift=int(rng.integers(1, 40)), axis=1)
+                self.host_ring[r, c] = torch.from_numpy(np.ascontiguousarray(img))
+        self.dev_ring = self.host_ring.cuda()
+        torch.cuda.synchronize()
+        self.NS = NS = max(1, min(6, args.inflight))
+        self.out_rows = [[(Detection * 100)() for _ in range(C)] for _ in range(NS)]
+        self.out_verd = [[np.zeros(100, np.uint32) for _ in range(C)] for _ in range(NS)]
+        self.stream = torch.cuda.Stream()
+        self.scatter_buf = None
+        self.scatter_events = []
+
+    def close(self):
+        self.det.engine.close()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_max(self, x):
+        from watsor_b200.parallel import max_over_ranks
+        return max_over_ranks(x, device='cuda')
+
+    # ---- device-resident frames (optionally delivered by the NCCL scatter from rank 0)
+    def enable_scatter(self):
+        torch = self.torch
+        self.scatter_buf = [torch.empty((self.C, H, W, 3), dtype=torch.uint8, device='cuda') for _ in range(self.NS)]
+        if self.rank == 0:
+            self.all_ring = [self.dev_ring.clone() for _ in range(self.world)]
+
+    def dev_ptrs(self, step, slot, time_scatter=False):
+        from watsor_b200.parallel import scatter_frames
+        r = step % self.ring
+        if self.scatter_buf is not None:
+            # the engine's frame scatter: rank 0 owns every camera's frame and NCCL-scatters each rank's
+            # batch over NVLink; slot `slot` was collected before, so its buffer is free to overwrite
+            src = [self.all_ring[g][r] for g in range(self.world)] if self.rank == 0 else None
+            if time_scatter:
+                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                scatter_frames(self.scatter_buf[slot], src, src=0)
+                e1.record(self.stream)
+                self.scatter_events.append((e0, e1))
+            else:
+                scatter_frames(self.scatter_buf[slot], src, src=0)
+            self.det.engine.stream_fence(self.stream.cuda_stream, 0)
+            return [self.scatter_buf[slot][c].data_ptr() for c in range(self.C)]
+        return [self.dev_ring[r, c].data_ptr() for c in range(self.C)]
+
+    def run_device_steps(self, n_steps, first, time_scatter=False):
+        det, NS = self.det, self.NS
+        for i in range(n_steps):
+            s = i % NS
+            if i >= NS:
+                det.collect(s, self.out_rows[s], self.out_verd[s])
+            det.submit(s, self.dev_ptrs(first + i, s, time_scatter), self.cam_ids, fuse_filters=True,
+                       frames_on_device=True)
+        for i in range(max(0, n_steps - NS), n_steps):
+            det.collect(i % NS, self.out_rows[i % NS], self.out_verd[i % NS])
+
+    def time_device(self, steps, first):
+        """CUDA events on a torch stream fenced against the library's slot streams on both sides; max over ranks.
+        The wall clock stops before the closing barrier (the NCCL barrier is not part of the loop)."""
+        torch = self.torch
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        ev0.record(self.stream)
+        self.det.engine.stream_fence(self.stream.cuda_stream, 0)
+        self.run_device_steps(steps, first, time_scatter=self.scatter_buf is not None)
+        self.det.engine.stream_fence(self.stream.cuda_stream, 1)
+        ev1.record(self.stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        self.barrier()
+        dev_ms = self.reduce_max(ev0.elapsed_time(ev1))
+        return dev_ms, t_wall
+
+    # ---- host frames in pinned memory through the public API
+    def run_host_steps(self, n_steps, first):
+        det, NS = self.det, self.NS
+        for i in range(n_steps):
+            s = i % NS
+            if i >= NS:
+                det.collect(s, self.out_rows[s], self.out_verd[s])
+            r = (first + i) % self.ring
+            det.submit(s, [self.host_ring[r, c].data_ptr() for c in range(self.C)], self.cam_ids, fuse_filters=True,
+                       frames_on_device=False)
+        for i in range(max(0, n_steps - NS), n_steps):
+            det.collect(i % NS, self.out_rows[i % NS], self.out_verd[i % NS])
+
+    def time_host(self, steps, first):
+        self.barrier()
+        t0 = time.perf_counter()
+        self.run_host_steps(steps, first)
+        self.torch.cuda.synchronize()
+        return self.reduce_max(time.perf_counter() - t0)
+
+    def measure(self, want_long=True):
+        """-> dict with value / e2e (+ *_long when the K-step region is shorter than --min-seconds)."""
+        args, world, C = self.args, self.world, self.C
+        self.torch.cuda.set_stream(self.stream)
+        warm = max(self.NS, args.warmup)
+        self.run_device_steps(warm, 0)
+        launches = self.det.engine.last_launch_count()
+        dev_ms, t_wall = self.time_device(args.steps, args.warmup)
+        out = {'value': world * C * args.steps / (dev_ms / 1e3), 'ms_per_step': dev_ms / args.steps,
+               'launches_per_step': launches, 'wall_ms_per_step_device_loop': 1e3 * t_wall / args.steps,
+               'detections_per_frame': float(np.mean([sum(1 for r in range(100) if rows[r].confidence > 0)
+                                                      for rows in self.out_rows[0]])),
+               'passed_filters_per_frame': float(np.mean([int(np.count_nonzero(v & 16)) for v in self.out_verd[0]]))}
+        long_steps = int(min(20000, max(args.steps, args.min_seconds * 1e3 / max(1e-3, out['ms_per_step']))))
+        if want_long and long_steps > args.steps:
+            ms, _ = self.time_device(long_steps, args.warmup + args.steps)
+            out['value_long'] = {'value': world * C * long_steps / (ms / 1e3), 'steps': long_steps,
+                                 'ms_per_step': ms / long_steps}
+        self.run_host_steps(warm, 0)
+        e2e_s = self.time_host(args.steps, args.warmup)
+        out['e2e_k'] = {'value': world * C * args.steps / e2e_s, 'steps': args.steps,
+                        'ms_per_step': 1e3 * e2e_s / args.steps}
+        e2e_steps = int(min(20000, max(args.steps, args.min_seconds / max(1e-6, e2e_s / args.steps))))
+        if want_long and e2e_steps > args.steps:
+            e2e_s = self.time_host(e2e_steps, args.warmup + args.steps)
+        else:
+            e2e_steps = args.steps
+        out['e2e'] = {'value': world * C * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': C * self.frame_bytes,
+                      'd2h_bytes_per_step': C * 100 * (72 + 4), 'ms_per_step': 1e3 * e2e_s / e2e_steps,
+                      'steps': e2e_steps,
+                      'api': 'watsor_b200.detection.b200.B200ObjectDetector.submit/collect (%d slots in flight), '
+                             'wall clock between barriers, max over ranks; timed over max(K, %.1f s) steps, '
+                             'the K-step figure is e2e_k' % (self.NS, args.min_seconds)}
+        return out
+
+    def measure_scatter(self, ms_per_step):
+        """The same device loop with every tick's frames NCCL-scattered from rank 0 (north star: 'NCCL over
+        NVLink only for the engine's frame scatter')."""
+        args, world, C = self.args, self.world, self.C
+        self.enable_scatter()
+        self.run_device_steps(max(self.NS, args.warmup), 0)
+        steps = int(min(5000, max(args.steps, 0.5e3 / max(1e-3, ms_per_step))))   # >= 0.5 s
+        self.scatter_events = []
+        dev_ms, _ = self.time_device(steps, args.warmup)
+        us = [1e3 * a.elapsed_time(b) for a, b in self.scatter_events]
+        rec = {'value': world * C * steps / (dev_ms / 1e3), 'steps': steps, 'ms_per_step': dev_ms / steps,
+               'nvlink_bytes_per_tick': (world - 1) * C * self.frame_bytes,
+               'scatter_us_median': float(np.median(us)) if us else None,
+               'scatter_us_p90': float(np.percentile(us, 90)) if us else None,
+               'collective': 'torch.distributed.scatter (ncclScatter: grouped send/recv) of [C,H,W,3] u8 per rank '
+                             'from rank 0; the kernels read the receive buffer in place'}
+        self.scatter_buf = None
+        return rec
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -251,14 +452,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # NUMA: bind this rank to the CPUs next to its GPU before any pinned allocation or thread creation
+    from watsor_b200.parallel import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)
+
     import torch
     import torch.distributed as dist
-
-    from watsor_b200 import _lib
-    from watsor_b200.detection.b200 import B200ObjectDetector
-    from watsor_b200.engine import PRECISION_BF16_TC, PRECISION_FP32
-    from watsor_b200.parallel import camera_shard, max_over_ranks, scatter_frames
-    from watsor_b200.stream.share import Detection
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl b200 needs a B200; there is no CPU fallback')
@@ -268,134 +467,41 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    model, model_desc = load_model(args.model)
-    C = args.cameras
-    precision = {'fp32': 0, 'bf16': 1, 'tf32x3': 2}[args.precision]
-    det = B200ObjectDetector(None, device=local_rank, max_batch=C, precision=precision, model_blob=model.to_blob())
-    for c in range(C):
-        det.configure_camera(c, W, H, camera_config(c))
-    cam_ids = list(range(C))
-
-    # input ring: distinct frames per camera, total > L2, so each step's input comes from HBM
-    frame_bytes = W * H * 3
-    ring = max(4, -(-int(1.4 * L2_BYTES) // (C * frame_bytes)))
-    base = [make_frames(args.frames, g, min(ring, 6)) for g in camera_shard(rank, world, C)]
-    host_ring = torch.empty((ring, C, H, W, 3), dtype=torch.uint8).pin_memory()
-    rng = np.random.default_rng(1234 + rank)
-    for r in range(ring):
-        for c in range(C):
-            img = base[c][r % len(base[c])]
-            if r >= len(base[c]):          # distinct bytes per ring slot: roll the picture a little
-                img = np.roll(img, shift=int(rng.integers(1, 40)), axis=1)
-            host_ring[r, c] = torch.from_numpy(np.ascontiguousarray(img))
-    dev_ring = host_ring.cuda()
-    torch.cuda.synchronize()
-
-    NS = max(1, min(6, args.inflight))
-    out_rows = [[(Detection * 100)() for _ in range(C)] for _ in range(NS)]
-    out_verd = [[np.zeros(100, np.uint32) for _ in range(C)] for _ in range(NS)]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max(x):
-        return max_over_ranks(x, device='cuda')
-
-    # ---------------- value: device-resident frames, device-timed.  Three batches are kept in flight on the
-    # library's slot streams (kernels of step k+1 fill the SMs the short tail layers of step k leave idle);
-    # the CUDA events live on a torch stream that is fenced against the slot streams on both sides.
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    scatter_buf = None
-    if args.ingest == 'scatter' and world > 1:
-        scatter_buf = [torch.empty((C, H, W, 3), dtype=torch.uint8, device='cuda') for _ in range(NS)]
-        if rank == 0:
-            all_ring = [dev_ring.clone() for _ in range(world)]
-
-    def dev_ptrs(step, slot):
-        r = step % ring
-        if scatter_buf is not None:
-            # the engine's frame scatter: rank 0 owns every camera's frame and NCCL-scatters each rank's
-            # batch over NVLink; slot `slot` was collected before, so its buffer is free to overwrite
-            src = [all_ring[g][r] for g in range(world)] if rank == 0 else None
-            scatter_frames(scatter_buf[slot], src, src=0)
-            det.engine.stream_fence(stream.cuda_stream, 0)
-            return [scatter_buf[slot][c].data_ptr() for c in range(C)]
-        return [dev_ring[r, c].data_ptr() for c in range(C)]
-
-    def run_device_steps(n_steps, first):
-        for i in range(n_steps):
-            s = i % NS
-            if i >= NS:
-                det.collect(s, out_rows[s], out_verd[s])
-            det.submit(s, dev_ptrs(first + i, s), cam_ids, fuse_filters=True, frames_on_device=True)
-        for i in range(max(0, n_steps - NS), n_steps):
-            det.collect(i % NS, out_rows[i % NS], out_verd[i % NS])
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    run_device_steps(max(NS, args.warmup), 0)
-    launches = det.engine.last_launch_count()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    det.engine.stream_fence(stream.cuda_stream, 0)
-    run_device_steps(args.steps, args.warmup)
-    det.engine.stream_fence(stream.cuda_stream, 1)
-    ev1.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    dev_ms = ev0.elapsed_time(ev1)
-    dev_ms = reduce_max(dev_ms)
-    value = world * C * args.steps / (dev_ms / 1e3)
-    detections_per_frame = float(np.mean([sum(1 for r in range(100) if rows[r].confidence > 0) for rows in out_rows[0]]))
-
-    # ---------------- e2e: host frames (pinned), public API, H2D + D2H inside the timed region
-    barrier()
-
-    def host_frames(step):
-        r = step % ring
-        return [host_ring[r, c].data_ptr() for c in range(C)]
-
-    def run_host_steps(n_steps, first):
-        for i in range(n_steps):
-            s = i % NS
-            if i >= NS:
-                det.collect(s, out_rows[s], out_verd[s])
-            det.submit(s, host_frames(first + i), cam_ids, fuse_filters=True, frames_on_device=False)
-        for i in range(max(0, n_steps - NS), n_steps):
-            det.collect(i % NS, out_rows[i % NS], out_verd[i % NS])
-
-    run_host_steps(max(NS, args.warmup), 0)
-    barrier()
-    t0 = time.perf_counter()
-    run_host_steps(args.steps, args.warmup)
-    torch.cuda.synchronize()
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    e2e_value = world * C * args.steps / e2e_s
+    arm = Arm(args, args.model, rank, local_rank, world, torch, dist)
+    if args.ingest == 'scatter' and world > 1:
+        arm.enable_scatter()
+    m = arm.measure()
+    scatter = None
+    if world > 1 and args.ingest == 'local' and not args.no_scatter:
+        scatter = arm.measure_scatter(m['ms_per_step'])
+        scatter['vs_local_ingest'] = scatter['value'] / (m.get('value_long') or m)['value']
     # keep the GPU loaded until nvidia-smi has a few samples (its first line takes ~0.3 s)
     t_load = time.perf_counter()
     extra = 0
-    while time.perf_counter() - t_load < 1.5:
-        run_host_steps(20, 0)
+    while time.perf_counter() - t_load < 1.0:
+        arm.run_host_steps(20, 0)
         extra += 20
     clocks = sampler.stop()
-    clocks['window'] = 'warm-up + timed device loop + timed e2e loop + %d extra e2e steps (100 ms period)' % extra
+    clocks['window'] = 'warm-up + every timed loop of the headline model + %d extra e2e steps (100 ms period)' % extra
 
     # ---------------- roofline of the dominant kernel + per-layer times (rank 0)
     roofline = None
     layer_table = None
     if rank == 0 and not args.no_roofline:
-        roofline, layer_table = measure_roofline(det, model, dev_ring, C, cam_ids, precision)
+        roofline, layer_table = measure_roofline(arm.det, arm.model, arm.dev_ring, arm.C, arm.cam_ids, arm.precision)
+
+    worker = None
+    if rank == 0 and not args.no_worker:
+        worker = measure_worker(args, local_rank, m)
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        run, cores, host_cores = oracle_step_fn(model, args)
-        pool = [(base[c][f], c) for f in range(2) for c in range(C)]
+        run, cores, host_cores = oracle_step_fn(arm.model, args)
+        C = arm.C
+        pool = [(arm.base[c][f], c) for f in range(2) for c in range(C)]
         run(*pool[0])
         t0 = time.perf_counter()
         done = 0
@@ -403,48 +509,82 @@ def main():
             run(*pool[done % len(pool)])
             done += 1
         dt = time.perf_counter() - t0
-        sample_frames = pool[:done] if done <= len(pool) else [None] * done
-        cpu_baseline = {'value': len(sample_frames) / dt, 'unit': UNIT, 'cores': cores, 'host_cores': host_cores,
+        cpu_baseline = {'value': done / dt, 'unit': UNIT, 'cores': cores, 'host_cores': host_cores,
                         'kind': 'port',
                         'sample': '%d frames (cycling the first ring slots of the %d cameras), batch 1, %.1f s of CPU work, torch threads calibrated; '
                                   'CPU restatement of the reference TF graph (oracle/), not TensorFlow'
-                                  % (len(sample_frames), C, dt)}
+                                  % (done, C, dt)}
+    arm.close()
+
+    # ---------------- second record: the only model with real weights (round 1's headline configuration)
+    real = None
+    if args.model != 'shapes' and not args.no_real_weights:
+        arm2 = Arm(args, 'shapes', rank, local_rank, world, torch, dist)
+        r = arm2.measure()
+        real = {'model': arm2.model_desc, 'workload': 'same frames; porch.png mask on camera 0, 3 labels',
+                'value': r['value'], 'ms_per_step': r['ms_per_step'], 'value_long': r.get('value_long'),
+                'e2e': r['e2e']['value'], 'e2e_steps': r['e2e']['steps'], 'launches_per_step': r['launches_per_step'],
+                'detections_per_frame': r['detections_per_frame']}
+        arm2.close()
 
     if rank == 0:
+        C = args.cameras
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16' if precision == 1 else 'f32', 'data': 'synthetic',
+            'metric': METRIC, 'value': m['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16' if arm.precision == 1 else 'f32', 'data': 'synthetic',
             'config': {
                 'workload': workload_name(args), 'cameras_per_gpu': C, 'global_batch': world * C,
-                'frame': '640x480x3 u8', 'model': model_desc, 'frames': args.frames, 'ingest': args.ingest,
-                'precision': args.precision, 'batches_in_flight': NS,
+                'frame': '640x480x3 u8', 'model': arm.model_desc, 'frames': args.frames, 'ingest': args.ingest,
+                'num_classes': arm.model.num_classes, 'score_threshold': arm.model.score_thr,
+                'masks': 'one per camera (cam 0: porch.png, 2 zones; cams 1..%d: synthetic RGBA, 1 + cam %% 4 zones)'
+                         % (C - 1) if args.model != 'shapes' else 'porch.png on camera 0',
+                'camera_to_gpu': 'camera c -> rank c // %d (contiguous blocks; BASELINE.md suggests c mod G, '
+                                 'equivalent for independent cameras)' % C,
+                'precision': args.precision, 'batches_in_flight': arm.NS,
                 'persistent_gemm_ctas': int(os.environ.get('WB_PERSIST_CTAS', '0')),
                 'l2': 'input ring of %d distinct frames per camera (%.0f MB per GPU) > 126 MB L2; no flush needed'
-                      % (ring, ring * C * frame_bytes / 1e6),
-                'detections_per_frame': detections_per_frame,
-                'wall_ms_per_step_device_loop': 1e3 * t_wall / args.steps,
+                      % (arm.ring, arm.ring * C * arm.frame_bytes / 1e6),
+                'detections_per_frame': m['detections_per_frame'],
+                'passed_filters_per_frame': m['passed_filters_per_frame'],
+                'wall_ms_per_step_device_loop': m['wall_ms_per_step_device_loop'],
+                'numa': numa,
+                'real_weights': real,
                 'per_layer_ms': layer_table,
             },
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': C * frame_bytes,
-                    'd2h_bytes_per_step': C * 100 * (72 + 4), 'ms_per_step': 1e3 * e2e_s / args.steps,
-                    'api': 'watsor_b200.detection.b200.B200ObjectDetector.submit/collect (%d slots in flight)' % NS},
-            'gpu_launches': launches * args.steps,
-            'gpu_launches_per_step': launches,
+            'value_long': m.get('value_long'),
+            'e2e': m['e2e'],
+            'e2e_k': m['e2e_k'],
+            'e2e_worker': worker,
+            'scatter': scatter,
+            'gpu_launches': m['launches_per_step'] * args.steps,
+            'gpu_launches_per_step': m['launches_per_step'],
             'clocks': clocks,
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
         }
         print(json.dumps(line), flush=True)
-    det.engine.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_worker(args, local_rank, headline):
+    """e2e through the drop-in worker (watsor_b200.detection.detector.ObjectDetector) on multiprocessing shared
+    frames; implemented in watsor_b200/bench_worker.py when present."""
+    try:
+        from watsor_b200.bench_worker import run_worker_bench
+    except ImportError:
+        return None
+    try:
+        return run_worker_bench(args, local_rank, camera_config, load_model, make_frames)
+    except Exception as e:          # the headline number must not die with the auxiliary one
+        return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
 def measure_roofline(det, model, dev_ring, C, cam_ids, precision):
     """Per-layer CUDA-event times (un-graphed run, median of 5) -> the kernel family with the largest
     share of the step is the dominant kernel; its roofline uses SURVEY.md 8(d) algorithmic FLOPs/bytes."""
-    from watsor_b200.model import OP_CONV, OP_DW, OP_HEAD, OP_NAMES, OP_PW, OP_STEM
+    from watsor_b200.model import OP_ADD, OP_CONV, OP_DW, OP_HEAD, OP_NAMES, OP_PW, OP_STEM
     runs = []
     for rep in range(6):
         ptrs = [dev_ring[rep % dev_ring.shape[0], c].data_ptr() for c in range(C)]
@@ -462,7 +602,7 @@ def measure_roofline(det, model, dev_ring, C, cam_ids, precision):
             name = OP_NAMES[k]
             flops = 2.0 * l.macs * C
             w_bytes = 4.0 * l.kh * l.kw * (l.in_c if k != OP_DW else 1) * l.out_c
-            in_b = (W * H * 3) if k == OP_STEM else l.in_h * l.in_w * l.in_c * elem
+            in_b = (W * H * 3) if k == OP_STEM else l.in_h * l.in_w * l.in_c * elem * (2 if k == OP_ADD else 1)
             out_b = l.out_h * l.out_w * l.out_c * (4 if k == OP_HEAD else elem)
             byts = C * (in_b + out_b) + w_bytes
             if k in (OP_PW, OP_CONV, OP_HEAD):
@@ -471,7 +611,8 @@ def measure_roofline(det, model, dev_ring, C, cam_ids, precision):
         f['ms'] += float(t)
         f['flops'] += flops
         f['bytes'] += byts
-        f['launches'] += 1 if k != 100 else 3
+        if float(t) > 0:
+            f['launches'] += 1 if k != 100 else 3
         table.append([name if k == 100 else model.layers[i].name[-28:], round(float(t), 4)])
     total = sum(f['ms'] for f in fam.values())
     dom = max(fam, key=lambda n: fam[n]['ms'])
@@ -489,19 +630,23 @@ def measure_roofline(det, model, dev_ring, C, cam_ids, precision):
     else:
         ach = d['bytes'] / (d['ms'] / 1e3) / 1e9
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm}
+    # DRAM bytes per launch of the dominant family from the committed ncu --set full capture of this model
+    # (profiles/r02_traffic.json: {model name: {precision: {family: {dram_bytes_per_launch}}}}), batch 8 only
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     prec_name = {0: 'fp32', 1: 'bf16', 2: 'tf32x3'}[precision]
-    if os.path.isfile(tp):
-        t = json.load(open(tp)).get(prec_name, {}).get(dom)
-        if t and C == 8:
-            traffic = t['dram_bytes_per_launch']     # ncu --set full, batch 8 (profiles/)
+    tp = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.isfile(tp) and C == 8:
+        t = json.load(open(tp)).get(model.name, {}).get(prec_name, {}).get(dom)
+        if t:
+            traffic = t['dram_bytes_per_launch']
     roof.update({'traffic': traffic, 'traffic_unit': 'bytes of DRAM read+write per launch (ncu capture in profiles/, batch 8)',
-                 'algorithmic_bytes_per_launch': d['bytes'] / d['launches'], 'kernel': {'gemm': 'k_gemm_tc / k_gemm_tc_persist / k_dwpw_tc_x3 (tcgen05 1x1 convs, fused dw+1x1, heads) + k_gemm_cc (3x3 extras)', 'dw': 'k_dw',
-                                             'stem': 'k_stem', 'post': 'k_decode_scores+k_nms+k_merge_filter'}.get(dom, dom),
+                 'algorithmic_bytes_per_launch': d['bytes'] / max(1, d['launches']),
+                 'kernel': {'gemm': 'tcgen05 GEMM family: k_gemm_tc / k_gemm_tc_persist / fused kernels (1x1 convs, 3x3 extras, heads)',
+                            'dw': 'k_dw_strip', 'stem': 'k_stem', 'add': 'k_add',
+                            'post': 'k_decode_scores+k_nms+k_merge_filter'}.get(dom, dom),
                  'peak_source': src, 'share_of_step': d['ms'] / total, 'launches_per_step': d['launches'],
                  'algorithmic_gflop_per_step': d['flops'] / 1e9, 'algorithmic_mb_per_step': d['bytes'] / 1e6,
-                 'avg_launch_us': 1e3 * d['ms'] / d['launches'],
+                 'avg_launch_us': 1e3 * d['ms'] / max(1, d['launches']),
                  'frac_of_mode_ceiling': (roof['achieved'] / (tf / {0: 1e9, 1: 1.0, 2: 6.0}[precision])
                                           if roof['bound'] == 'tensor' else None),
                  'families_ms': {n: round(f['ms'], 4) for n, f in fam.items()},
@@ -509,7 +654,7 @@ def measure_roofline(det, model, dev_ring, C, cam_ids, precision):
                                        if f['ms'] > 0},
                  'note': 'per-layer CUDA events, every layer launched 10x back to back (median of 5 runs); '
                          'TF32X3 issues 3 TF32 MMAs per product, so its tensor ceiling is bf16 peak/6 (frac_of_mode_ceiling); '
-                         'the k-loop is shared-memory-port bound (profiles/r01_pipeline_trace.md); traffic from ncu is in profiles/'})
+                         'traffic from ncu is in profiles/'})
     return roof, table
 
 

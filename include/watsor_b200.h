@@ -73,7 +73,9 @@ int wb_device_count(int* count);
 /* replaces TensorRTObjectDetector.__init__ / __enter__ (watsor/detection/tensorrt_gpu.py:23-57) and
  * TensorFlowObjectDetector.__init__ (tensorflow_cpu.py:13-25): builds the device-resident model from
  * a compiled model blob (watsor_b200/model.py writes it from frozen_inference_graph.pb / cpu.pb).
- * precision: 0 = fp32 CUDA-core path (parity mode), 1 = bf16 tcgen05 tensor-core path. */
+ * precision: 0 = fp32 storage, dense convs on CUDA cores (FFMA); 1 = bf16 storage, tcgen05 kind::f16 (fast mode, not
+ * a parity mode); 2 = fp32 storage, dense convs as 3xTF32 tcgen05 MMAs with fp32 accumulation (fp32-faithful: the
+ * default of the Python host and what bench.py reports); 3 = single TF32 MMA (diagnostic). */
 int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_batch, int precision,
               wb_ctx** out);
 /* replaces __exit__ (tensorrt_gpu.py:59-63) */

@@ -135,15 +135,17 @@ def test_post_edge_cases(engine, shapes_oracle):
     assert not mism
 
 
-def test_post_coco_heads_90_classes(coco_model):
-    """90-class heads, threshold 1e-8 (every anchor is a candidate in every class)."""
+@pytest.mark.parametrize('precision', [0, 2], ids=['fp32-cuda-cores', 'fp32-3xtf32-tcgen05'])
+def test_post_coco_heads_90_classes(coco_model, precision):
+    """90-class heads, threshold 1e-8 (every anchor is a candidate in every class); the post stage is the same
+    code in every precision mode, run here in both the reported one and the CUDA-core one."""
     from oracle.ssd_model import SsdModelOracle
     oracle = SsdModelOracle(coco_model)
     rng = np.random.default_rng(11)
     n = oracle.num_anchors
     enc = (rng.standard_normal((n, 4)) * 0.8).astype(np.float32)
     lg = (rng.standard_normal((n, 91)) * 1.5 - 3.0).astype(np.float32)
-    with Engine(coco_model.to_blob(), device=0, max_batch=2, precision=0) as e:
+    with Engine(coco_model.to_blob(), device=0, max_batch=2, precision=precision) as e:
         e.set_camera(0, 640, 480)
         cnt, mism = check_post(e, oracle, enc, lg)
         assert cnt == 100 and not mism, mism[:3]

@@ -562,7 +562,7 @@ def synthetic_ssd_mobilenet_v1(num_classes=90, seed=0, score_thr=1e-8, input_siz
     return m
 
 
-def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_size=300):
+def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_size=300, cls_gain=0.3, cls_bias=-4.5):
     """SSD-MobileNet-v2 architecture descriptor (TF-slim mobilenet_v2, depth multiplier 1.0, plus the
     SSD feature-map layout of ssd_mobilenet_v2_feature_extractor: taps `layer_15/expansion_output`
     19x19x576 and `layer_19` 10x10x1280, then four 1x1 -> 3x3/s2 extra pairs 512/256/256/128) with
@@ -571,6 +571,12 @@ def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_siz
 
     Inverted residual block: 1x1 expand (x6, BN, ReLU6) -> 3x3 depthwise (stride s, BN, ReLU6) ->
     1x1 linear projection (BN), residual add when stride == 1 and channels match.
+
+    `cls_gain` / `cls_bias` shape the class logits like a trained detector's: with plain He weights the logits
+    of this random net have std 3.7 around -2, i.e. thousands of (anchor, class) scores saturate at 1.0 - 6e-8 and
+    the top-100 list is a block of exact fp32 ties.  Gain 0.3 / bias -4.5 gives logits ~ N(-4.5, 1.2^2): almost
+    every score is ~0.01 (they all still pass the 1e-8 threshold, so the per-class NMS sees all 1917 anchors in
+    every class, as with the zoo models), and the tail reaches 0.4 .. 0.8 in a handful of classes.
     """
     rng = np.random.default_rng(seed)
     m = Model(name='ssd_mobilenet_v2_synthetic_c%d' % num_classes, input_h=input_size, input_w=input_size,
@@ -638,8 +644,8 @@ def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_siz
         n0 = len(m.layers)
         row += em.head('BoxPredictor_%d' % k, f, he((1, 1, c, a * 4), c) * 0.5,
                        (0.05 * rng.standard_normal(a * 4)).astype(np.float32),
-                       he((1, 1, c, a * (num_classes + 1)), c),
-                       (-2.0 + 0.5 * rng.standard_normal(a * (num_classes + 1))).astype(np.float32),
+                       he((1, 1, c, a * (num_classes + 1)), c) * np.float32(cls_gain),
+                       (cls_bias + 0.5 * rng.standard_normal(a * (num_classes + 1))).astype(np.float32),
                        row, num_classes + 1)
         head_layers.append(m.layers.pop(n0))
     for hl in head_layers:

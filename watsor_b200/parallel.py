@@ -40,3 +40,72 @@ def sum_over_ranks(value, device='cpu'):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def gpu_cpu_affinity(device_index):
+    """CPUs on the NUMA node next to GPU `device_index` (the `nvidia-smi topo -m` "CPU Affinity" column), or
+    None when it cannot be determined.  NVML first, then sysfs `local_cpulist` of the GPU's PCI function."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(device_index))
+            words = (len(__import__('os').sched_getaffinity(0)) + 4096) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+            if cpus:
+                return cpus
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        pass
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bdf) as f:
+            return parse_cpulist(f.read())
+    except Exception:
+        return None
+
+
+def _physical_index(device_index):
+    """NVML enumerates physical GPUs; CUDA_VISIBLE_DEVICES may renumber them for this process."""
+    import os
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        ids = [v.strip() for v in vis.split(',') if v.strip()]
+        if device_index < len(ids) and ids[device_index].isdigit():
+            return int(ids[device_index])
+    return device_index
+
+
+def parse_cpulist(text):
+    """'0-31,64-95' -> {0..31, 64..95}"""
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs local to its GPU, so that the pinned ingest ring is allocated on (and
+    the submitting thread runs on) the NUMA node the GPU's PCIe root hangs off.  Eight unbound ranks doing 7.4 MB
+    of H2D per 0.4 ms from the wrong socket cost 23 % of the end-to-end rate at 8 GPUs in round 1.  Returns a
+    short description for the bench record; never raises."""
+    import os
+    try:
+        cpus = gpu_cpu_affinity(device_index)
+        allowed = os.sched_getaffinity(0)
+        if not cpus:
+            return 'unbound (no affinity information)'
+        use = cpus & allowed
+        if not use or use == allowed:
+            return 'unbound (GPU-local CPUs = all allowed CPUs, %d)' % len(allowed)
+        os.sched_setaffinity(0, use)
+        return 'bound to %d GPU-local CPUs (%d..%d)' % (len(use), min(use), max(use))
+    except Exception as e:           # affinity is an optimisation, never a failure
+        return 'unbound (%s)' % type(e).__name__
