@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -78,6 +80,18 @@ struct wb_ctx {
   bool has_user_stream = false;
   int last_launches = 0;
   std::vector<void*> registered;
+  // One lock for everything that touches shared per-context state: the camera table (h_cams / d_cams / SATs), slot 0's
+  // staging buffers used by the stage-level calls, the filter staging buffers and the registration list.  The
+  // reference runs one DetectionSieve thread per camera in one process (ref: watsor/main.py:378-384) and ctypes drops
+  // the GIL, so wb_filter_rows / wb_set_camera DO get called concurrently.  Held for the host-side enqueue only,
+  // except in the synchronous calls (filter_rows, set_camera, stage-level test hooks), which hold it until their
+  // results are back.
+  std::mutex mu;
+  // wb_filter_rows: its own stream and staging buffers (never slot 0's: a detector batch may be in flight there)
+  cudaStream_t fstream = nullptr;
+  wb_detection* d_frows = nullptr;
+  uint32_t* d_fverd = nullptr;
+  int frows_cap = 0;
 
   const float* tensor(int idx) const { return d_weights + tensors[idx].offset; }
   size_t elem_size() const { return precision == 1 ? 2 : 4; }
@@ -138,7 +152,11 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   REQUIRE(precision >= 0 && precision <= 3,
           "precision must be 0 (fp32 CUDA cores), 1 (bf16 tcgen05), 2 (fp32 via 3xTF32 tcgen05) or 3 (1xTF32, diagnostic)");
   CK(cudaSetDevice(device));
-  wb_ctx* c = new wb_ctx();
+  struct CtxFree {
+    void operator()(wb_ctx* p) const { wb_destroy(p); }
+  };
+  std::unique_ptr<wb_ctx, CtxFree> guard(new wb_ctx());  // every REQUIRE / CK early return below frees it
+  wb_ctx* c = guard.get();
   c->device = device;
   c->max_batch = max_batch;
   c->precision = precision;
@@ -202,8 +220,12 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
   CK(cudaMemset(c->d_cams, 0, sizeof(CameraCfg) * WB_MAX_CAMERAS));
   for (int s = 0; s < WB_SLOTS; ++s)
     if (alloc_slot(c, c->slots[s])) return 1;
+  c->frows_cap = WB_MAX_DETECTIONS * max_batch;
+  CK(cudaStreamCreateWithFlags(&c->fstream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&c->d_frows, sizeof(wb_detection) * (size_t)c->frows_cap));
+  CK(cudaMalloc(&c->d_fverd, sizeof(uint32_t) * (size_t)c->frows_cap));
   CK(cudaDeviceSynchronize());
-  *out = c;
+  *out = guard.release();
   return 0;
 }
 
@@ -241,6 +263,9 @@ int wb_destroy(wb_ctx* c) {
   }
   for (auto* p : c->cam_sat) cudaFree(p);
   cudaFree(c->d_cams);
+  cudaFree(c->d_frows);
+  cudaFree(c->d_fverd);
+  if (c->fstream) cudaStreamDestroy(c->fstream);
   cudaFree(c->d_weights);
   tc_free_weights(&c->tc);
   delete c;
@@ -288,6 +313,7 @@ int wb_set_camera(wb_ctx* c, int cam, int width, int height, int n_zones, const 
   REQUIRE(n_zones >= 0 && n_zones <= WB_MAX_CAMERA_ZONES, "a mask may hold at most 32 zones");
   REQUIRE(n_zones == 0 || raster != nullptr, "zone_raster is NULL");
   REQUIRE(n_filters == 0 || filters != nullptr, "filters is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());  // no batch may be reading the table while it changes
   CameraCfg cfg;
@@ -340,6 +366,7 @@ int wb_set_camera(wb_ctx* c, int cam, int width, int height, int n_zones, const 
 
 int wb_register_host(wb_ctx* c, void* ptr, size_t bytes) {
   REQUIRE(c && ptr && bytes, "NULL argument");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
   c->registered.push_back(ptr);
@@ -347,6 +374,7 @@ int wb_register_host(wb_ctx* c, void* ptr, size_t bytes) {
 }
 int wb_unregister_host(wb_ctx* c, void* ptr) {
   REQUIRE(c && ptr, "NULL argument");
+  std::lock_guard<std::mutex> lock(c->mu);
   for (size_t i = 0; i < c->registered.size(); ++i)
     if (c->registered[i] == ptr) {
       CK(cudaHostUnregister(ptr));
@@ -518,6 +546,7 @@ int wb_submit(wb_ctx* c, int slot, int n, const uint8_t* const* frames, const in
   REQUIRE(c && frames && cam_ids, "NULL argument");
   REQUIRE(slot >= 0 && slot < WB_SLOTS, "slot out of range");
   REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range (1..max_batch)");
+  std::lock_guard<std::mutex> lock(c->mu);
   Slot& s = c->slots[slot];
   REQUIRE(!s.busy, "slot is busy: collect it first");
   CK(cudaSetDevice(c->device));
@@ -543,10 +572,13 @@ int wb_collect(wb_ctx* c, int slot, wb_detection* const* out, uint32_t* const* v
   REQUIRE(c, "NULL ctx");
   REQUIRE(slot >= 0 && slot < WB_SLOTS, "slot out of range");
   Slot& s = c->slots[slot];
-  REQUIRE(s.busy, "slot has no batch in flight");
+  {
+    std::lock_guard<std::mutex> lock(c->mu);
+    REQUIRE(s.busy, "slot has no batch in flight");
+    s.busy = false;
+  }
   CK(cudaSetDevice(c->device));
-  s.busy = false;
-  CK(cudaEventSynchronize(s.ev1));
+  CK(cudaEventSynchronize(s.ev1));  // not under the lock: other threads keep submitting to other slots
   if (gpu_ms) CK(cudaEventElapsedTime(gpu_ms, s.ev0, s.ev1));
   if (s.flags & WB_F_OUT_ON_DEVICE) {
     cudaStream_t st = c->stream_of(slot);
@@ -601,6 +633,7 @@ int wb_preprocess(wb_ctx* c, int n, const uint8_t* const* frames, const int32_t*
                   float* out) {
   REQUIRE(c && frames && widths && heights && out, "NULL argument");
   REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   REQUIRE(!s.busy, "slot 0 is busy");
@@ -634,6 +667,7 @@ int wb_backbone(wb_ctx* c, int n, const float* pre, float* enc, float* logits, i
   REQUIRE(c && pre, "NULL argument");
   REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
   REQUIRE(stop_layer < (int)c->layers.size(), "stop_layer out of range");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   REQUIRE(!s.busy, "slot 0 is busy");
@@ -676,6 +710,7 @@ int wb_postprocess(wb_ctx* c, int n, const float* enc, const float* logits, cons
                    int32_t* num) {
   REQUIRE(c && enc && logits && cam_ids, "NULL argument");
   REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   REQUIRE(!s.busy, "slot 0 is busy");
@@ -707,18 +742,19 @@ int wb_postprocess(wb_ctx* c, int n, const float* enc, const float* logits, cons
 
 int wb_filter_rows(wb_ctx* c, int cam, int n_rows, wb_detection* rows, uint32_t* verdicts) {
   REQUIRE(c && rows && verdicts, "NULL argument");
+  REQUIRE(n_rows >= 1 && n_rows <= c->frows_cap, "n_rows out of range");
+  // thread-safe: one DetectionSieve thread per camera calls this concurrently (ref: watsor/main.py:378-384)
+  std::lock_guard<std::mutex> lock(c->mu);
   REQUIRE(cam >= 0 && cam < WB_MAX_CAMERAS && c->h_cams[cam].width > 0, "camera has not been configured");
-  REQUIRE(n_rows >= 1 && n_rows <= WB_MAX_DETECTIONS * c->max_batch, "n_rows out of range");
   CK(cudaSetDevice(c->device));
-  Slot& s = c->slots[0];
-  REQUIRE(!s.busy, "slot 0 is busy");
-  cudaStream_t st = c->stream_of(0);
-  CK(cudaMemcpyAsync(s.d_out, rows, sizeof(wb_detection) * n_rows, cudaMemcpyHostToDevice, st));
-  LaunchCtx lc{st, &s.launches};
-  launch_filter_rows(lc, c->d_cams + cam, n_rows, s.d_out, s.d_verdicts);
+  cudaStream_t st = c->fstream;
+  CK(cudaMemcpyAsync(c->d_frows, rows, sizeof(wb_detection) * n_rows, cudaMemcpyHostToDevice, st));
+  int launches = 0;
+  LaunchCtx lc{st, &launches};
+  launch_filter_rows(lc, c->d_cams + cam, n_rows, c->d_frows, c->d_fverd);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(rows, s.d_out, sizeof(wb_detection) * n_rows, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(verdicts, s.d_verdicts, sizeof(uint32_t) * n_rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rows, c->d_frows, sizeof(wb_detection) * n_rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(verdicts, c->d_fverd, sizeof(uint32_t) * n_rows, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -735,6 +771,7 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
                       float* ms, int32_t* kinds, int max_launches, int* n_out) {
   REQUIRE(c && device_frames && cam_ids && ms && kinds && n_out, "NULL argument");
   REQUIRE(n >= 1 && n <= c->max_batch, "batch size out of range");
+  std::lock_guard<std::mutex> lock(c->mu);
   CK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   REQUIRE(!s.busy, "slot 0 is busy");

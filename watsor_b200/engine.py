@@ -91,12 +91,13 @@ class Engine:
             arr[i] = ClassFilter(label, 1 if zones else 0, bits, 0, conf, area)
         n_zones = 0
         raster_ptr = None
+        dummy = np.zeros(1, np.uint8)          # stays alive until wb_set_camera has returned
         if zone_rasters is not None:
             zone_rasters = np.ascontiguousarray(zone_rasters, dtype=np.uint8)
             assert zone_rasters.ndim == 3 and zone_rasters.shape[1:] == (height, width)
             n_zones = zone_rasters.shape[0]
             # a mask without any zone is still "has_mask" (MaskFilter would reject everything)
-            raster_ptr = zone_rasters.ctypes.data if n_zones else np.zeros(1, np.uint8).ctypes.data
+            raster_ptr = zone_rasters.ctypes.data if n_zones else dummy.ctypes.data
         check(self.lib.wb_set_camera(self._ctx, cam_id, width, height, n_zones, raster_ptr,
                                      len(class_filters), arr, flags))
         self.cameras[cam_id] = (width, height)
