@@ -112,3 +112,30 @@ def test_residual_add_keeps_both_inputs_alive():
     check_arena(m)
     add = [l for l in m.layers if l.op == OP_ADD][0]
     assert add.in_off != add.in2_off
+
+
+@needs_ref
+def test_older_nms_exports_are_refused_not_miscompiled(tmp_path):
+    """A graph whose post-processing is not the NonMaxSuppressionV5 topology (the 2018 model-zoo exports clip and
+    filter per class before NonMaxSuppressionV2/V3) must raise instead of compiling with the wrong semantics."""
+    from tensorboard.compat.proto import graph_pb2
+    g = graph_pb2.GraphDef()
+    with open(REF_PB, 'rb') as f:
+        g.ParseFromString(f.read())
+    for n in g.node:
+        if n.op == 'NonMaxSuppressionV5':
+            n.op = 'NonMaxSuppressionV3'
+    p = tmp_path / 'old_export.pb'
+    p.write_bytes(g.SerializeToString())
+    with pytest.raises(NotImplementedError, match='NonMaxSuppressionV3'):
+        compile_frozen_graph(str(p))
+    # a per-class ClipToWindow_k in front of the NMS nodes is refused as well
+    g.ParseFromString(open(REF_PB, 'rb').read())
+    scope = next(n.name for n in g.node if n.op == 'NonMaxSuppressionV5').split('non_max_suppression')[0]
+    extra = g.node.add()
+    extra.name = scope + 'ClipToWindow_7/Minimum'
+    extra.op = 'Identity'
+    extra.input.append(scope + 'Minimum/x')
+    p.write_bytes(g.SerializeToString())
+    with pytest.raises(NotImplementedError, match='ClipToWindow_7'):
+        compile_frozen_graph(str(p))

@@ -429,15 +429,36 @@ def compile_frozen_graph(pb_path, name=None):
     m.scale_h = float(g.const(d + 'truediv_2/y'))
     m.scale_w = float(g.const(d + 'truediv_3/y'))
     m.logit_scale = float(g.const('Postprocessor/scale_logits/y'))
-    nms = g.ops('NonMaxSuppressionV5') or g.ops('NonMaxSuppressionV3') or g.ops('NonMaxSuppressionV2')
+    nms = g.ops('NonMaxSuppressionV5')
     if not nms:
+        old = g.ops('NonMaxSuppressionV4') + g.ops('NonMaxSuppressionV3') + g.ops('NonMaxSuppressionV2') + \
+            g.ops('NonMaxSuppression')
+        if old:
+            # e.g. the 2018 model-zoo exports (ssd_mobilenet_v1_coco_2018_01_28): per class they run
+            # FilterGreaterThan_k and ClipToWindow_k BEFORE NonMaxSuppressionV2/V3, i.e. IoU on clipped boxes and the
+            # score threshold as a separate Greater node.  The CUDA post stage implements the newer export order
+            # (NMS on unclipped boxes -> sort -> ClipToWindow -> prune -> top-k); compiling such a graph silently
+            # would change detections for boxes that cross the image border.
+            raise NotImplementedError(
+                'this graph uses %s (an older TF Object-Detection export with clip-before-NMS); only the '
+                'NonMaxSuppressionV5 post-processing topology is implemented' % g.nodes[old[0]].op)
         raise ValueError('no NonMaxSuppression node found')
-    ins = g.nodes[nms[0]].data_inputs()
-    m.iou_thr = float(g.const(ins[3][0]))
-    m.score_thr = float(g.const(ins[4][0])) if len(ins) > 4 else 0.0
-    if len(ins) > 5 and float(g.const(ins[5][0])) != 0.0:
-        raise NotImplementedError('soft-NMS')
     scope = nms[0].split('non_max_suppression')[0]
+    per_class_pre = [n for n in g.order if n.startswith(scope) and
+                     (n[len(scope):].startswith('ClipToWindow_') or n[len(scope):].startswith('FilterGreaterThan'))]
+    if per_class_pre:
+        raise NotImplementedError('per-class %s before the NMS node: clip/filter-before-NMS export order is not '
+                                  'implemented' % per_class_pre[0][len(scope):].split('/')[0])
+    if len(nms) != m.num_classes:
+        raise NotImplementedError('expected one NonMaxSuppressionV5 per class (%d), found %d'
+                                  % (m.num_classes, len(nms)))
+    ins = g.nodes[nms[0]].data_inputs()
+    if len(ins) < 6:
+        raise ValueError('NonMaxSuppressionV5 with %d inputs' % len(ins))
+    m.iou_thr = float(g.const(ins[3][0]))
+    m.score_thr = float(g.const(ins[4][0]))
+    if float(g.const(ins[5][0])) != 0.0:
+        raise NotImplementedError('soft-NMS')
     m.max_per_class = int(g.const(scope + 'Minimum/x'))
     total = [n for n in g.order if n.startswith(scope) and n.endswith('/x') and
              g.nodes[n].op == 'Const' and '/Minimum_' in n]
