@@ -33,10 +33,27 @@ struct TcArgs {
   int block_n, stages, k_blocks;
   int splits, kb_per;  // split-K over blockIdx.z (partials reduced by k_splitk_reduce)
   float* partial;      // [splits][M][n_pad]
+  int* tile_counters;  // split-K: arrival ticket per output tile (zero on entry, reset by the last-arriving CTA)
+  const void* residual;  // != NULL: y = (acc*scale + offset) + residual[m][n]  (MobileNet-v2 bottleneck `Add`)
+  // KxK / strided convolutions: the A tile of k-block kb is the tap (kb / cpb) of the filter window, channel block
+  // kb % cpb, fetched by a 4-D TMA box {32 ch, OW, OH, imgs} whose traversal strides are the conv stride
+  int conv, cpb, conv_kw, conv_pad_t, conv_pad_l;
+  int rows_per_tile;  // GEMM rows one CTA produces (128, or imgs_per_tile*OH*OW for conv tiles)
   int ta_stages;  // > 0: A operand staged in tensor memory (k_gemm_tc<2, true>), ring of 64-column hi/lo pairs
   int n_main;  // TF32X3: the hi*hi products rotate over n_main TMEM accumulators (+1 for the corrections)
   int act, is_head, anchors_per_loc, row_off, n_box, num_anchors, ncp1, hw;
 };
+
+__device__ __forceinline__ void tma_load_4d_tc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// barrier among the four epilogue warps only (128 threads, hardware barrier 1)
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // MODE 0: bf16 operands; MODE 1: tf32 single product (diagnostic); MODE 2: tf32 x3 split
 // TA (TF32X3 only, experimental, WB_TMEM_A=1): the converter warps write the hi / lo rows into tensor memory
@@ -66,8 +83,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   uint64_t* ta_empty = ta_conv + 4;   // [4] TA: MMAs done with a TMEM stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * g.block_n;
+  const int m0 = blockIdx.x * g.rows_per_tile, n0 = blockIdx.y * g.block_n;
   const int kb0 = blockIdx.z * g.kb_per;
+  __shared__ int s_ticket;
   const int nkb = min(g.k_blocks, kb0 + g.kb_per) - kb0;  // k-blocks of this split (>= 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
   const int n_acc = X3 ? g.n_main + 1 : 1;
@@ -107,8 +125,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         WB_STAMP(0, it);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t bar = smem_u32(&full[s]);
-        mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
-        tma_load_2d(smem_u32(st), &map_a, bar, kb * K_PER_BLOCK, m0);
+        if (g.conv) {
+          // rows_per_tile = imgs * OH * OW rows arrive (the box never leaves the image range: whole images per tile);
+          // taps that fall outside the input are zero-filled by TMA = TF SAME padding
+          mbar_expect_tx(bar, g.rows_per_tile * ROW_BYTES + b_tile_bytes * (X3 ? 2 : 1));
+          const int tap = kb / g.cpb, cb = kb - tap * g.cpb;
+          const int ky = tap / g.conv_kw, kx = tap - ky * g.conv_kw;
+          tma_load_4d_tc(smem_u32(st), &map_a, bar, cb * K_PER_BLOCK, kx - g.conv_pad_l, ky - g.conv_pad_t, m0 / g.hw);
+        } else {
+          mbar_expect_tx(bar, A_TILE_BYTES + b_tile_bytes * (X3 ? 2 : 1));
+          tma_load_2d(smem_u32(st), &map_a, bar, kb * K_PER_BLOCK, m0);
+        }
         uint8_t* sb = st + A_TILE_BYTES * A_SLOTS;
         tma_load_2d(smem_u32(sb), &map_b, bar, kb * K_PER_BLOCK, n0);
         if (X3) tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bar, kb * K_PER_BLOCK, n0);
@@ -171,9 +198,82 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int m = m0 + row;
+    const bool row_ok = row < g.rows_per_tile && m < g.M;
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
     if (threadIdx.x == 64) WB_STAMP(5, 0);
+    if (g.splits > 1) {
+      // split-K: raw partial accumulators -> scratch; the LAST CTA to arrive at this output tile adds the partial
+      // tiles in split order (z = 0, 1, ...: the order does not depend on who arrives when, so the result is
+      // deterministic and bit-identical to the former two-kernel reduce) and runs the layer epilogue.
+      for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+        uint32_t v[16];
+        load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
+                       min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
+        const int n = n0 + c0;
+        if (!row_ok || n >= g.n_pad) continue;
+        float* pp = g.partial + ((size_t)blockIdx.z * g.M + m) * g.n_pad + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          __stcg(reinterpret_cast<float4*>(pp + j), make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+      }
+      __threadfence();
+      epilogue_bar_sync();
+      const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+      if (threadIdx.x == 64) s_ticket = atomicAdd(&g.tile_counters[tile_id], 1);
+      epilogue_bar_sync();
+      if (s_ticket == g.splits - 1) {
+        __threadfence();
+        const int et = threadIdx.x - 64;  // 0..127
+        const int c4n = g.block_n >> 2;
+        const int rows = min(g.rows_per_tile, g.M - m0);
+        for (int idx = et; idx < rows * c4n; idx += 128) {
+          const int r = idx / c4n, n = n0 + (idx - r * c4n) * 4;
+          if (n >= g.N) continue;
+          const int mm = m0 + r;
+          float4 acc = __ldcg(reinterpret_cast<const float4*>(g.partial + (size_t)mm * g.n_pad + n));
+          for (int z = 1; z < g.splits; ++z) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(g.partial + ((size_t)z * g.M + mm) * g.n_pad + n));
+            acc.x = __fadd_rn(acc.x, p.x);
+            acc.y = __fadd_rn(acc.y, p.y);
+            acc.z = __fadd_rn(acc.z, p.z);
+            acc.w = __fadd_rn(acc.w, p.w);
+          }
+          float y[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = affine_rn(y[j], __ldg(g.scale + n + j), __ldg(g.offset + n + j));
+            y[j] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+          }
+          if (g.is_head) {
+            const int f = mm / g.hw;
+            const size_t hr = (size_t)f * g.num_anchors + g.row_off + (size_t)(mm - f * g.hw) * g.anchors_per_loc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int nn = n + j;
+              if (nn >= g.N) break;
+              if (nn < g.n_box)
+                g.enc[hr * 4 + nn] = y[j];
+              else
+                g.logits[hr * g.ncp1 + (nn - g.n_box)] = y[j];
+            }
+          } else if (TF32) {
+            if (g.residual != nullptr) {
+              const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (size_t)mm * g.N + n);
+              y[0] = __fadd_rn(y[0], rr.x);
+              y[1] = __fadd_rn(y[1], rr.y);
+              y[2] = __fadd_rn(y[2], rr.z);
+              y[3] = __fadd_rn(y[3], rr.w);
+            }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)mm * g.N + n) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+            ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)mm * g.N + n, make_float4(y[0], y[1], y[2], y[3]));
+          }
+        }
+        if (threadIdx.x == 64) g.tile_counters[tile_id] = 0;  // ready for the next launch (stream-ordered)
+      }
+    } else {
     const int f = g.is_head ? m / g.hw : 0;
     const size_t head_row = g.is_head ? (size_t)f * g.num_anchors + g.row_off + (size_t)(m - f * g.hw) * g.anchors_per_loc : 0;
     for (int c0 = 0; c0 < g.block_n; c0 += 16) {
@@ -181,15 +281,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
                      min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
       const int n = n0 + c0;
-      if (m >= g.M || n >= g.N) continue;
-      if (g.splits > 1) {
-        float* pp = g.partial + ((size_t)blockIdx.z * g.M + m) * g.n_pad + n;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(pp + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        continue;
-      }
+      if (!row_ok || n >= g.N) continue;
       float y[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -210,9 +302,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         }
       } else if (TF32) {
         float* o = reinterpret_cast<float*>(g.out) + (size_t)m * g.N + n;
+        const float* rs = g.residual != nullptr ? reinterpret_cast<const float*>(g.residual) + (size_t)m * g.N + n : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
-          if (n + j < g.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          if (n + j < g.N) {
+            float4 yy = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            if (rs != nullptr) {
+              const float4 rr = *reinterpret_cast<const float4*>(rs + j);
+              yy = make_float4(__fadd_rn(yy.x, rr.x), __fadd_rn(yy.y, rr.y), __fadd_rn(yy.z, rr.z), __fadd_rn(yy.w, rr.w));
+            }
+            *reinterpret_cast<float4*>(o + j) = yy;
+          }
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)m * g.N + n;
 #pragma unroll
@@ -228,6 +328,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
             *reinterpret_cast<uint4*>(o + j) = pk;
           }
       }
+    }
     }
     if (threadIdx.x == 64) WB_STAMP(6, 0);
   } else if (X3) {
@@ -437,6 +538,18 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
             float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
             y[h * 32 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
           }
+          if (TF32 && g.residual != nullptr && m0 + q * 32 + lane < g.M) {
+            // MobileNet-v2 bottleneck `Add` fused behind the linear projection: (conv*scale + offset) + shortcut
+            const float* rs = reinterpret_cast<const float*>(g.residual) + (size_t)(m0 + q * 32 + lane) * g.N + n0 + c0 + h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(rs + i);
+              y[h * 32 + i + 0] = __fadd_rn(y[h * 32 + i + 0], rr.x);
+              y[h * 32 + i + 1] = __fadd_rn(y[h * 32 + i + 1], rr.y);
+              y[h * 32 + i + 2] = __fadd_rn(y[h * 32 + i + 2], rr.z);
+              y[h * 32 + i + 3] = __fadd_rn(y[h * 32 + i + 3], rr.w);
+            }
+          }
         }
         // staging buffer (chunk_no & 1) was last used two chunks ago: its TMA store must have read it
         if (chunk_no >= 2) {
@@ -577,7 +690,8 @@ bool make_out_map(CUtensorMap* map, void* base, int elem_bytes, int rows, int n,
 }  // namespace
 
 bool tc_encode_map(void* map, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
-                   const unsigned long long* strides_bytes, const unsigned* box, bool swizzle128, std::string* err) {
+                   const unsigned long long* strides_bytes, const unsigned* box, bool swizzle128, std::string* err,
+                   const unsigned* elem_strides) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     *err = "cuTensorMapEncodeTiled is not available from the driver";
@@ -588,7 +702,7 @@ bool tc_encode_map(void* map, const void* base, int elem_bytes, int rank, const 
   for (int i = 0; i < rank; ++i) {
     d[i] = dims[i];
     b[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) st[i] = strides_bytes[i];
   }
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(map),
@@ -615,7 +729,11 @@ int pick_block_n(int n_pad) {
 }  // namespace
 
 bool tc_layer_supported(const wb_layer& L) {
-  return (L.op == WB_OP_PW || L.op == WB_OP_HEAD) && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.in_c % 4 == 0;
+  if ((L.op == WB_OP_PW || L.op == WB_OP_HEAD) && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.in_c % 4 == 0) return true;
+  // KxK / strided dense convolutions (the SSD extra layers): implicit GEMM, one filter tap x 32 (64 bf16) channels
+  // per k-block; a CTA's tile is a whole number of output images, so the maps must be small (<= 128 pixels)
+  return L.op == WB_OP_CONV && L.in_c % 64 == 0 && L.out_h * L.out_w <= (uint32_t)BLOCK_M && L.stride <= 8 &&
+         getenv("WB_NO_TC_CONV") == nullptr;
 }
 
 int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb_tensor_entry>& tensors,
@@ -626,7 +744,7 @@ int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb
     const wb_layer& L = layers[li];
     if (!tc_layer_supported(L)) continue;
     TcLayerWeights& w = out->layers[li];
-    const int K = L.in_c, NP = L.n_pad;
+    const int K = L.kh * L.kw * L.in_c, NP = L.n_pad;             // conv: k = tap * in_c + channel
     const float* src = host_data + tensors[L.w_tensor].offset;  // [K][NP]
     w.k = K;
     w.n_pad = NP;
@@ -686,7 +804,8 @@ void tc_free_weights(TcWeights* w) {
 
 int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, int n, const wb_layer& L, const void* in,
                    const float* scale, const float* offset, void* out, float* enc, float* logits, int num_anchors,
-                   int num_classes_p1, float* partial, size_t partial_floats, std::string* err) {
+                   int num_classes_p1, float* partial, size_t partial_floats, int* tile_counters, const void* residual,
+                   std::string* err) {
   const TcLayerWeights& w = tw.layers[layer_index];
   if (!w.ready) {
     *err = "no tensor-core weights for this layer";
@@ -703,8 +822,20 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.M = n * L.out_h * L.out_w;
   g.N = L.out_c;
   g.n_pad = L.n_pad;
-  g.K = L.in_c;
+  g.K = L.kh * L.kw * L.in_c;
   g.block_n = w.block_n;
+  g.tile_counters = tile_counters;
+  g.residual = mode == TC_BF16 ? nullptr : residual;
+  g.conv = L.op == WB_OP_CONV;
+  g.cpb = (L.in_c * elem) / ROW_BYTES;
+  g.conv_kw = L.kw;
+  g.conv_pad_t = L.pad_t;
+  g.conv_pad_l = L.pad_l;
+  g.rows_per_tile = g.conv ? (BLOCK_M / (int)(L.out_h * L.out_w)) * (int)(L.out_h * L.out_w) : BLOCK_M;
+  if (mode == TC_BF16 && residual != nullptr) {
+    *err = "residual fusion is not available in bf16 mode";
+    return 1;
+  }
   g.k_blocks = (g.K * elem + ROW_BYTES - 1) / ROW_BYTES;
   g.act = L.act;
   g.is_head = L.op == WB_OP_HEAD;
@@ -718,13 +849,13 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.n_main = 1;
   g.ta_stages = 0;
   int stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
-  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.n_pad + g.block_n - 1) / g.block_n);
+  dim3 grid((g.M + g.rows_per_tile - 1) / g.rows_per_tile, (g.n_pad + g.block_n - 1) / g.block_n);
   // latency-bound shapes: split K so that about one wave of CTAs exists (deterministic two-pass reduce)
   g.splits = 1;
   g.kb_per = g.k_blocks;
   g.partial = partial;
   const long tiles = (long)grid.x * grid.y;
-  if (partial != nullptr && tiles < 74 && g.k_blocks >= 4) {
+  if (partial != nullptr && tile_counters != nullptr && tiles < 74 && tiles <= 4096 && g.k_blocks >= 4) {
     int want = (int)((148 + tiles - 1) / tiles);  // ~one CTA per SM of a B200
     int splits = std::min(want, g.k_blocks / 2);
     while (splits > 1 && (size_t)splits * g.M * g.n_pad > partial_floats) --splits;
@@ -743,7 +874,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  bool persist = !g.is_head && g.splits == 1 && tiles >= num_sms && g.N == g.n_pad && g.block_n % cw == 0 &&
+  bool persist = !g.is_head && !g.conv && g.splits == 1 && tiles >= num_sms && g.N == g.n_pad && g.block_n % cw == 0 &&
                  g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
   if (persist && mode == TC_TF32X3) {
     g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
@@ -764,7 +895,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       // accumulator halves the TMEM footprint, so two such CTAs can share an SM
       if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;
     }
-    if (mode == TC_TF32X3 && getenv("WB_TMEM_A") != nullptr) {
+    if (mode == TC_TF32X3 && !g.conv && getenv("WB_TMEM_A") != nullptr) {
       // experimental: A ring in tensor memory; chains of <= 32 steps per main accumulator
       const int steps = g.kb_per * (ROW_BYTES / UMMA_K_BYTES);
       const int nm = steps <= 32 ? 1 : (steps <= 64 ? 2 : 3);
@@ -782,8 +913,20 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   if (stages < 1) stages = 1;
   g.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
-  CUtensorMap map_a;
-  if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) return 1;
+  alignas(64) CUtensorMap map_a;
+  if (g.conv) {
+    const int imgs = BLOCK_M / (int)(L.out_h * L.out_w);
+    unsigned long long dims[4] = {L.in_c, L.in_w, L.in_h, (unsigned long long)n};
+    unsigned long long st[3] = {(unsigned long long)L.in_c * elem, (unsigned long long)L.in_w * L.in_c * elem,
+                                (unsigned long long)L.in_h * L.in_w * L.in_c * elem};
+    // boxDim counts tensor elements traversed; ceil(boxDim / elementStride) elements are loaded per dimension
+    unsigned box[4] = {(unsigned)(ROW_BYTES / elem), (unsigned)((L.out_w - 1) * L.stride + 1),
+                       (unsigned)((L.out_h - 1) * L.stride + 1), (unsigned)imgs};
+    unsigned es[4] = {1, L.stride, L.stride, 1};
+    if (!tc_encode_map(&map_a, in, elem, 4, dims, st, box, true, err, es)) return 1;
+  } else if (!make_map(&map_a, in, elem, g.M, g.K, BLOCK_M, err)) {
+    return 1;
+  }
   CUtensorMap map_b, map_b_lo;
   if (g.block_n == w.block_n) {
     memcpy(&map_b, w.tmap_b, sizeof(map_b));
@@ -851,29 +994,6 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     return 1;
   }
   ++*lc.launch_counter;
-  if (g.splits > 1) {
-    SplitKReduceArgs r;
-    r.partial = partial;
-    r.scale = scale;
-    r.offset = offset;
-    r.out = out;
-    r.out_is_bf16 = mode == TC_BF16;
-    r.enc = enc;
-    r.logits = logits;
-    r.M = g.M;
-    r.N = g.N;
-    r.ld = g.n_pad;
-    r.splits = g.splits;
-    r.act = g.act;
-    r.is_head = g.is_head;
-    r.anchors_per_loc = g.anchors_per_loc;
-    r.row_off = g.row_off;
-    r.n_box = g.n_box;
-    r.num_anchors = g.num_anchors;
-    r.ncp1 = g.ncp1;
-    r.hw = g.hw;
-    launch_splitk_reduce(lc, r);
-  }
   return 0;
 }
 

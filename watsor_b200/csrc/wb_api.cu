@@ -44,6 +44,7 @@ struct Slot {
   float *d_enc = nullptr, *d_logits = nullptr, *d_dec = nullptr;
   float* d_partial = nullptr;  // split-K scratch
   size_t partial_floats = 0;
+  int* d_tile_counters = nullptr;  // split-K arrival tickets (zero between launches)
   int *d_cand_count = nullptr, *d_sel_count = nullptr;
   unsigned long long *d_cand = nullptr, *d_sel = nullptr;
   wb_detection *d_out = nullptr, *h_out = nullptr;
@@ -129,6 +130,8 @@ static int alloc_slot(wb_ctx* c, Slot& s) {
   CK(cudaMalloc(&s.d_dec, sizeof(float) * (size_t)B * N * 4));
   s.partial_floats = (size_t)4 * 1024 * 1024 + (size_t)B * 512 * 1024;
   CK(cudaMalloc(&s.d_partial, sizeof(float) * s.partial_floats));
+  CK(cudaMalloc(&s.d_tile_counters, sizeof(int) * 4096));
+  CK(cudaMemset(s.d_tile_counters, 0, sizeof(int) * 4096));
   CK(cudaMalloc(&s.d_cand_count, sizeof(int) * (size_t)B * C));
   CK(cudaMalloc(&s.d_sel_count, sizeof(int) * (size_t)B * C));
   CK(cudaMalloc(&s.d_cand, sizeof(unsigned long long) * (size_t)B * C * N));
@@ -244,6 +247,7 @@ int wb_destroy(wb_ctx* c) {
     cudaFree(s.d_logits);
     cudaFree(s.d_dec);
     cudaFree(s.d_partial);
+    cudaFree(s.d_tile_counters);
     cudaFree(s.d_cand_count);
     cudaFree(s.d_sel_count);
     cudaFree(s.d_cand);
@@ -433,10 +437,30 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
       case WB_OP_CONV:
       case WB_OP_HEAD:
         if (c->precision != 0 && tc_layer_supported(L)) {
+          // MobileNet-v2 bottleneck: a linear projection followed by `Add(shortcut, projection)` runs as one kernel,
+          // the shortcut is added in the GEMM epilogue (fp32 modes) and the Add layer is skipped
+          const void* residual = nullptr;
+          void* dst = static_cast<void*>(outp);
+          bool fuse_add = false;
+          if (c->precision != 1 && L.op == WB_OP_PW && L.act == WB_ACT_NONE && li + 1 < end && getenv("WB_NO_FUSE_ADD") == nullptr) {
+            const wb_layer& A = c->layers[li + 1];
+            // the fused kernel reads this layer's input while it writes the Add's output: they must not overlap
+            // (model.py plan_arena keeps the input alive through the Add; older blobs may not)
+            const unsigned long long a0 = L.in_off, a1 = a0 + (unsigned long long)L.in_h * L.in_w * L.in_c;
+            const unsigned long long b0 = A.out_off, b1 = b0 + (unsigned long long)A.out_h * A.out_w * A.out_c;
+            if (A.op == WB_OP_ADD && (A.in_off == L.out_off || A.in2_off == L.out_off) && A.in_off != A.in2_off &&
+                !(a0 < b1 && b0 < a1)) {
+              const uint32_t other = A.in_off == L.out_off ? A.in2_off : A.in_off;
+              residual = static_cast<const void*>(arena + (size_t)other * n);
+              dst = static_cast<void*>(arena + (size_t)A.out_off * n);
+              fuse_add = true;
+            }
+          }
           std::string err;
-          if (tc_launch_gemm(lc, c->tc, (int)li, n, L, static_cast<const void*>(in), sc, of, static_cast<void*>(outp),
-                             s.d_enc, s.d_logits, NA, C1, s.d_partial, s.partial_floats, &err))
+          if (tc_launch_gemm(lc, c->tc, (int)li, n, L, static_cast<const void*>(in), sc, of, dst, s.d_enc, s.d_logits, NA,
+                             C1, s.d_partial, s.partial_floats, s.d_tile_counters, residual, &err))
             return fail("layer " + std::string(L.name) + ": " + err);
+          if (fuse_add) ++li;  // the Add layer is done
         } else {
           launch_gemm_cc<T>(lc, n, L, in, w, sc, of, outp, s.d_enc, s.d_logits, NA, C1, s.d_partial, s.partial_floats);
         }
@@ -796,8 +820,16 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
         c->layers[li + 1].in_off == c->layers[li].out_off &&
         fused_dwpw_supported(c->tc, li + 1, c->layers[li], c->layers[li + 1], n))
       last = li + 1;
+    // a linear projection + residual Add pair runs as one kernel too (same conditions as run_layers); the
+    // pair's time is reported on the Add entry, the projection entry reads 0
+    if (last == li && c->precision != 0 && c->precision != 1 && li + 1 < nl && c->layers[li].op == WB_OP_PW &&
+        c->layers[li].act == WB_ACT_NONE && c->layers[li + 1].op == WB_OP_ADD && tc_layer_supported(c->layers[li]) &&
+        (c->layers[li + 1].in_off == c->layers[li].out_off || c->layers[li + 1].in2_off == c->layers[li].out_off) &&
+        getenv("WB_NO_FUSE_ADD") == nullptr)
+      last = li + 1;
     const int first = li;
-    if (last != li) {
+    const bool time_on_first = last != li && c->layers[li].op == WB_OP_PW;  // projection + Add: time on the GEMM
+    if (last != li && !time_on_first) {
       CK(cudaEventRecord(ev[li + 1], st));  // zero-length interval for the depthwise entry
       kinds[li] = (int)c->layers[li].op;
       ++li;
@@ -809,6 +841,11 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
     }
     CK(cudaEventRecord(ev[li + 1], st));
     kinds[li] = (int)c->layers[li].op;
+    if (time_on_first) {
+      ++li;
+      CK(cudaEventRecord(ev[li + 1], st));  // zero-length interval for the Add entry
+      kinds[li] = (int)c->layers[li].op;
+    }
   }
   for (int r = 0; r < REPS; ++r)
     if (int rc = run_post(c, s, st, n, 0)) return rc;

@@ -126,6 +126,13 @@ class Model:
             nxt = self.layers[i + 1]
             if l.op == OP_DW and nxt.op == OP_PW and nxt.src == l.dst and l.src:
                 last_use[l.src] = max(last_use[l.src], i + 1)
+        # a linear 1x1 projection followed by the residual `Add` of its output runs as one kernel (the shortcut is
+        # added in the GEMM epilogue, csrc/wb_api.cu run_layers): that kernel reads the projection's INPUT while it
+        # writes the Add's OUTPUT, so the input must outlive the Add layer
+        for i, l in enumerate(self.layers[:-1]):
+            nxt = self.layers[i + 1]
+            if l.op == OP_PW and nxt.op == OP_ADD and l.dst in (nxt.src, nxt.src2) and l.src:
+                last_use[l.src] = max(last_use[l.src], i + 1)
         size = {}
         for l in self.layers:
             if l.dst:
