@@ -117,8 +117,10 @@ def _check_frame(got, img, o32, o64, stats, to_detections, analyse, compare_with
 
 @pytest.mark.parametrize('precision', **PRECISIONS)
 def test_configs2_heads_vs_float64(v2coco, precision):
-    """Raw head tensors of the 90-class v2 net: the GPU is as close to the float64 evaluation of the same
-    layer program as the fp32 CPU oracle is (within 3x), and within 2e-4 absolute."""
+    """Raw head tensors of the 90-class v2 net (53 conv layers deep, logits of magnitude ~8) against the float64
+    evaluation of the same layer program: within 5e-4 absolute (a confidence error <= 1.3e-4, the north star allows
+    1e-3) and within 4x of the fp32 CPU oracle's own distance from float64 (measured: CUDA cores 1x, 3xTF32 3x --
+    the tensor core accumulates with truncation)."""
     m, o32, o64, frames = v2coco
     with Engine(m.to_blob(), device=0, max_batch=2, precision=precision) as e:
         for fr in frames[:3]:
@@ -126,7 +128,7 @@ def test_configs2_heads_vs_float64(v2coco, precision):
             (e32, l32), (e64, l64) = fr['heads32'], fr['heads64']
             for g, a, b in ((genc[0], e32, e64), (glg[0], l32, l64)):
                 err_gpu, err_cpu = np.abs(g - b).max(), np.abs(a - b).max()
-                assert err_gpu <= 2e-4 and err_gpu <= 3 * err_cpu + 2e-5, (err_gpu, err_cpu)
+                assert err_gpu <= 5e-4 and err_gpu <= 4 * err_cpu + 2e-5, (err_gpu, err_cpu)
 
 
 @pytest.mark.parametrize('precision', **PRECISIONS)

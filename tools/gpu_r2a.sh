@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/smi.txt 2>&1
 echo "== pytest -m gpu"
-timeout 1500 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40 > gpurun_out/r2a_pytest.log; tail -15 gpurun_out/r2a_pytest.log
+timeout 1800 python -m pytest tests -m gpu --maxfail=8 -q -s 2>&1 | tail -150 > gpurun_out/r2a_pytest.log; tail -25 gpurun_out/r2a_pytest.log
 echo "== bench (default = configs[2])"
 timeout 900 python bench.py --steps 200 --warmup 10 2> gpurun_out/r2a_bench.err | tail -1 > gpurun_out/r2a_bench.json; cut -c1-600 gpurun_out/r2a_bench.json; tail -3 gpurun_out/r2a_bench.err
 echo "== ncu launch list (one batch in flight)"

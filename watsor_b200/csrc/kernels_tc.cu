@@ -721,9 +721,16 @@ namespace {
 
 int pick_block_n(int n_pad) {
   if (n_pad <= 128) return n_pad;  // multiples of 16 up to 128: one N tile
+  int best = 16;
   for (int bn = 128; bn >= 16; bn -= 16)
-    if (n_pad % bn == 0) return bn;  // largest UMMA width (multiple of 16) that tiles N exactly
-  return 16;
+    if (n_pad % bn == 0) {
+      best = bn;  // largest UMMA width (multiple of 16) that tiles N exactly
+      break;
+    }
+  // N = 144 (MobileNet-v2 24 -> 144 expansions) only tiles as 3 x 48: three CTAs per row block re-reading the A tile
+  // and running three prologues/epilogues.  One UMMA may be up to 256 columns wide: use a single N tile instead.
+  if (best < 64 && n_pad <= 256) return n_pad;
+  return best;
 }
 
 }  // namespace
