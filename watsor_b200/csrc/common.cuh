@@ -129,7 +129,7 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
                  const float* anchors, const FrameDesc* frames, const CameraCfg* cams, uint32_t flags,
                  float* dec_boxes, int* cand_count, unsigned long long* cand, int* sel_count,
                  unsigned long long* sel, wb_detection* out, uint32_t* verdicts, float* raw_boxes,
-                 float* raw_scores, float* raw_classes, int* raw_num);
+                 float* raw_scores, float* raw_classes, int* raw_num, int* kept_hist);
 void launch_filter_rows(const LaunchCtx& lc, const CameraCfg* cam, int n_rows, wb_detection* rows,
                         uint32_t* verdicts);
 void launch_build_sat(const LaunchCtx& lc, const uint8_t* raster, int n_zones, int h, int w, int32_t* sat);

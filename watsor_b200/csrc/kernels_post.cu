@@ -9,6 +9,8 @@
 // Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in the graph's op
 // order, so that given identical head outputs the result is bit-identical to the oracle
 // (up to the last-ulp difference between CUDA's expf and the host libm's).
+#include <algorithm>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------- K7
@@ -160,13 +162,18 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* a, int P) {
 //     suppresses the later candidates of the same round that it overlaps.
 // Output: merge keys  score_bits << 32 | (0xFFFF - class) << 16 | (0xFFFF - rank)  for the kept boxes whose
 // window-clipped area is positive (0 otherwise), plus the anchor index of every kept box.
+constexpr int KEPT_BINS = 1024;
+// monotone non-decreasing in the score (scores are sigmoid outputs in [0, 1]); resolution 1/1024
+__device__ __forceinline__ int score_bin(unsigned score_bits) {
+  return min(KEPT_BINS - 1, max(0, (int)(__uint_as_float(score_bits) * (float)KEPT_BINS)));
+}
 constexpr int NMS_HEAD = 384;
 constexpr int NMS_PREFILTER_MIN = 640;
 
 __global__ void __launch_bounds__(256)
     k_nms(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ cand_count,
           const unsigned long long* __restrict__ cand, int sort_cap, int* __restrict__ sel_count,
-          unsigned long long* __restrict__ sel_key, int* __restrict__ sel_idx) {
+          unsigned long long* __restrict__ sel_key, int* __restrict__ sel_idx, int* __restrict__ kept_hist) {
   extern __shared__ unsigned long long s_dyn[];  // [2][sort_cap]: high segment, low segment
   unsigned long long* s_a = s_dyn;
   unsigned long long* s_b = s_dyn + sort_cap;
@@ -178,6 +185,8 @@ __global__ void __launch_bounds__(256)
   __shared__ unsigned s_alive;   // bit i: candidate i of the round survived phase 1
   __shared__ int s_nkept_sh, s_na, s_nb, s_cut;
   __shared__ int s_hist[1024];
+  __shared__ int s_above[8];
+  int* fhist = kept_hist + (size_t)blockIdx.y * KEPT_BINS;  // this frame's histogram of kept, selectable scores
   const int c = blockIdx.x, f = blockIdx.y, C = pp.num_classes, N = pp.num_anchors;
   const int n = min(cand_count[f * C + c], N);
   const int max_out = min(pp.max_per_class, N);
@@ -251,7 +260,8 @@ __global__ void __launch_bounds__(256)
   const float4* fdec = dec + (size_t)f * N;
   if (threadIdx.x == 0) s_nkept_sh = 0;
   __syncthreads();
-  for (int seg = 0; seg < 2; ++seg) {
+  bool stop = false;
+  for (int seg = 0; seg < 2 && !stop; ++seg) {
     const unsigned long long* sorted = seg == 0 ? s_a : s_b;
     const int count = seg == 0 ? n_a : n_b;
     if (seg == 1) {
@@ -265,6 +275,30 @@ __global__ void __launch_bounds__(256)
     for (int base = 0; base < count; base += 32) {
       const int nkept = s_nkept_sh;
       if (nkept >= max_out) break;
+      if (base > 0 || seg > 0) {
+        // Early exit (exact): the frame-wide histogram counts boxes that some class has already KEPT with a positive
+        // clipped area -- final facts.  If max_total of them sit in score bins strictly above this class's best
+        // remaining candidate, neither it nor anything after it can reach the frame's top max_total, and whatever
+        // this class would still select is never read.  Stale (smaller) counts only delay the exit.
+        const int b = score_bin((unsigned)(sorted[base] >> 32));
+        int above = 0;
+        for (int i = threadIdx.x * 4; i < KEPT_BINS; i += blockDim.x * 4) {
+          const int4 h = __ldcg(reinterpret_cast<const int4*>(fhist + i));
+          above += (i > b ? h.x : 0) + (i + 1 > b ? h.y : 0) + (i + 2 > b ? h.z : 0) + (i + 3 > b ? h.w : 0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+        if (lane == 0) s_above[warp] = above;
+        __syncthreads();
+        above = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) above += s_above[w];
+        __syncthreads();
+        if (above >= pp.max_total) {
+          stop = true;
+          break;
+        }
+      }
       const int cnt = min(32, count - base);
       if (threadIdx.x < 32) {
         if (lane < cnt) {
@@ -313,6 +347,7 @@ __global__ void __launch_bounds__(256)
             out_key[nk] = area > 0.f ? ((key & 0xFFFFFFFF00000000ull) | ((unsigned long long)(0xFFFFu - (unsigned)c) << 16) |
                                         (unsigned long long)(0xFFFFu - (unsigned)nk))
                                      : 0ull;
+            if (area > 0.f) atomicAdd(&fhist[score_bin((unsigned)(key >> 32))], 1);
           }
           ++nk;
           const bool hit = lane > t && lane < cnt && suppresses(box, barea, bt, at, pp.iou_thr);
@@ -394,73 +429,104 @@ __device__ uint32_t apply_filters(const CameraCfg* __restrict__ cam, wb_detectio
   return v | WB_V_PASS;
 }
 
-// One block per frame.  (1) merge keys of all classes -> shared memory; (2) warp 0 does the C-way
-// merge of the per-class sorted lists = `SortByField` (TopKV2, ties -> lower concat index) restricted
-// to boxes with positive clipped area, top max_total; (3) one thread per output row: clip, `add` +1,
-// tensorflow_cpu.py:79-90 integer conversion, predicates, Detection write.
-__global__ void __launch_bounds__(256)
+// One block per frame.  (1) the merge keys of all classes (C x max_per_class, zero = not selectable) are streamed
+// once: a 2048-bin histogram of their top bits finds the bin that holds the max_total-th largest key; (2) the keys at or
+// above that bin (normally ~max_total of them) are gathered into shared memory and sorted descending (bitonic) =
+// `SortByField` (TopKV2, ties -> lower concat index: the keys carry (class, rank) below the score, so they are distinct
+// and the descending key order IS the C-way merge order of the per-class lists) restricted to boxes with positive
+// clipped area, top max_total; (3) one thread per output row: clip, `add` +1, tensorflow_cpu.py:79-90 integer
+// conversion, predicates, Detection write.
+constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_BINS = 2048;   // sign + exponent + 2 mantissa bits of the score
+constexpr int MERGE_CAP = 4096;    // gathered keys that fit the fast path (ties in the cut bin can exceed max_total)
+
+__global__ void __launch_bounds__(MERGE_THREADS)
     k_merge_filter(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ sel_count,
                    const unsigned long long* __restrict__ sel_key, const int* __restrict__ sel_idx,
                    const FrameDesc* __restrict__ frames, const CameraCfg* __restrict__ cams, uint32_t flags,
                    wb_detection* __restrict__ out, uint32_t* __restrict__ verdicts, float* __restrict__ raw_boxes,
                    float* __restrict__ raw_scores, float* __restrict__ raw_classes, int* __restrict__ raw_num) {
-  extern __shared__ unsigned long long s_all[];  // [C][max_per_class]
+  extern __shared__ unsigned long long s_keys[];  // [cap]: gathered keys (cap = MERGE_CAP, or all keys in the slow path)
+  __shared__ int s_hist[MERGE_BINS];
   __shared__ unsigned long long s_win[128];
-  __shared__ int s_nvalid;
+  __shared__ int s_nvalid, s_cut, s_n;
   const int f = blockIdx.x, C = pp.num_classes, MP = pp.max_per_class, N = pp.num_anchors;
   const unsigned long long* keys = sel_key + (size_t)f * C * MP;
-  {
-    const int total = C * MP;
-    int i = threadIdx.x;
-    for (; i + 3 * (int)blockDim.x < total; i += 4 * blockDim.x) {  // 4 independent loads in flight per thread
-      const unsigned long long k0 = keys[i], k1 = keys[i + blockDim.x], k2 = keys[i + 2 * blockDim.x],
-                               k3 = keys[i + 3 * blockDim.x];
-      s_all[i] = k0;
-      s_all[i + blockDim.x] = k1;
-      s_all[i + 2 * blockDim.x] = k2;
-      s_all[i + 3 * blockDim.x] = k3;
-    }
-    for (; i < total; i += blockDim.x) s_all[i] = keys[i];
+  const int total = C * MP;
+  const int want = min(pp.max_total, 128);
+  for (int i = threadIdx.x; i < MERGE_BINS; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // keys beyond a class's selection count were zeroed by k_nms, so the whole [C][MP] block can be read blindly
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const unsigned long long k = __ldg(keys + i);
+    if (k != 0ull) atomicAdd(&s_hist[(int)(k >> 53)], 1);
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 32) {  // highest bins first until `want` keys are covered
     const int lane = threadIdx.x;
-    int ptr[4], cnt[4];
+    int acc = 0, cut = 0;
+    for (int top = MERGE_BINS - 1; top >= 0 && acc < want; top -= 32) {
+      const int b = top - lane;
+      const int v = b >= 0 ? s_hist[b] : 0;
+      int incl = v;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int c = lane + 32 * t;
-      cnt[t] = c < C ? sel_count[f * C + c] : 0;
-      ptr[t] = 0;
-      while (ptr[t] < cnt[t] && s_all[c * MP + ptr[t]] == 0ull) ++ptr[t];
-    }
-    int r = 0;
-    for (; r < pp.max_total; ++r) {
-      unsigned long long best = 0ull;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        int c = lane + 32 * t;
-        if (ptr[t] < cnt[t]) best = max(best, s_all[c * MP + ptr[t]]);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
-      // 64-bit max over the warp as two 32-bit hardware reductions: the score word first, then the
-      // (class, rank) word among the lanes that hold the winning score
-      const unsigned hi = (unsigned)(best >> 32);
-      const unsigned m_hi = __reduce_max_sync(0xffffffffu, hi);
-      const unsigned m_lo = __reduce_max_sync(0xffffffffu, hi == m_hi ? (unsigned)best : 0u);
-      best = ((unsigned long long)m_hi << 32) | m_lo;
-      if (best == 0ull) break;
-      int c = 0xFFFF - (int)((best >> 16) & 0xFFFFull);
-      if ((c & 31) == lane) {
-        int t = c >> 5;
-#pragma unroll
-        for (int tt = 0; tt < 4; ++tt)
-          if (tt == t) {
-            ++ptr[tt];
-            while (ptr[tt] < cnt[tt] && s_all[c * MP + ptr[tt]] == 0ull) ++ptr[tt];
-          }
-        s_win[r] = best;
+      const unsigned reach = __ballot_sync(0xffffffffu, acc + incl >= want);
+      if (reach) {
+        cut = top - (__ffs(reach) - 1);
+        acc = want;
+        break;
       }
+      acc += __shfl_sync(0xffffffffu, incl, 31);
+      cut = max(top - 31, 0);
     }
-    if (lane == 0) s_nvalid = r;
+    if (lane == 0) s_cut = cut;
+  }
+  __syncthreads();
+  const int cut = s_cut;
+  int cap = MERGE_CAP;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const unsigned long long k = __ldg(keys + i);  // second pass, L2 / L1 resident
+    if (k != 0ull && (int)(k >> 53) >= cut) {
+      const int p = atomicAdd(&s_n, 1);
+      if (p < cap) s_keys[p] = k;
+    }
+  }
+  __syncthreads();
+  int n_g = s_n;
+  if (n_g > cap) {
+    // pathological: thousands of keys share the cut bin (e.g. every score identical).  Sort everything; the
+    // dynamic shared memory was sized for the whole [C][MP] block by the launcher.
+    __syncthreads();
+    int P = 32;
+    while (P < total) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < total ? __ldg(keys + i) : 0ull;
+    n_g = total;
+    __syncthreads();
+    bitonic_desc(s_keys, P);
+  } else {
+    int P = 32;
+    while (P < n_g) P <<= 1;
+    for (int i = n_g + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = 0ull;
+    __syncthreads();
+    bitonic_desc(s_keys, P);
+  }
+  if (threadIdx.x < 128) {
+    const unsigned long long k = threadIdx.x < min(n_g, want) ? s_keys[threadIdx.x] : 0ull;
+    s_win[threadIdx.x] = k;
+  }
+  if (threadIdx.x == 0) {
+    // number of valid rows = non-zero keys among the first `want` (zeros sort last)
+    int lo = 0, hi = min(n_g, want);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_keys[mid] != 0ull) lo = mid + 1; else hi = mid;
+    }
+    s_nvalid = lo;
   }
   __syncthreads();
   const int nvalid = s_nvalid;
@@ -504,9 +570,10 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
                  const float* anchors, const FrameDesc* frames, const CameraCfg* cams, uint32_t flags,
                  float* dec_boxes, int* cand_count, unsigned long long* cand, int* sel_count,
                  unsigned long long* sel, wb_detection* out, uint32_t* verdicts, float* raw_boxes,
-                 float* raw_scores, float* raw_classes, int* raw_num) {
+                 float* raw_scores, float* raw_classes, int* raw_num, int* kept_hist) {
   const int C = pp.num_classes, N = pp.num_anchors;
   cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)n * C, lc.stream);
+  cudaMemsetAsync(kept_hist, 0, sizeof(int) * (size_t)n * KEPT_BINS, lc.stream);
   dim3 g1((N + DEC_TILE - 1) / DEC_TILE, n);
   const size_t dec_smem = (size_t)DEC_TILE * (C + 1) * (sizeof(float) + sizeof(short)) + 2 * sizeof(int) * C + 16;
   k_decode_scores<<<g1, 256, dec_smem, lc.stream>>>(pp, enc, logits, anchors, reinterpret_cast<float4*>(dec_boxes),
@@ -525,11 +592,16 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
     attr_done.set();
   }
   k_nms<<<dim3(C, n), 256, 2 * sizeof(unsigned long long) * sort_cap, lc.stream>>>(
-      pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx);
+      pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx, kept_hist);
   ++*lc.launch_counter;
-  k_merge_filter<<<n, 256, sizeof(unsigned long long) * (size_t)C * pp.max_per_class, lc.stream>>>(
-      pp, reinterpret_cast<const float4*>(dec_boxes), sel_count, sel_key, sel_idx, frames, cams, flags, out,
-      verdicts, raw_boxes, raw_scores, raw_classes, raw_num);
+  {
+    int P = 32;
+    while (P < C * pp.max_per_class) P <<= 1;
+    const size_t merge_smem = sizeof(unsigned long long) * (size_t)std::max(P, MERGE_CAP);
+    k_merge_filter<<<n, MERGE_THREADS, merge_smem, lc.stream>>>(
+        pp, reinterpret_cast<const float4*>(dec_boxes), sel_count, sel_key, sel_idx, frames, cams, flags, out,
+        verdicts, raw_boxes, raw_scores, raw_classes, raw_num);
+  }
   ++*lc.launch_counter;
 }
 

@@ -46,6 +46,7 @@ struct Slot {
   size_t partial_floats = 0;
   int* d_tile_counters = nullptr;  // split-K arrival tickets (zero between launches)
   int *d_cand_count = nullptr, *d_sel_count = nullptr;
+  int* d_kept_hist = nullptr;  // [B][1024] per-frame histogram of kept scores (exact NMS early exit)
   unsigned long long *d_cand = nullptr, *d_sel = nullptr;
   wb_detection *d_out = nullptr, *h_out = nullptr;
   uint32_t *d_verdicts = nullptr, *h_verdicts = nullptr;
@@ -134,6 +135,7 @@ static int alloc_slot(wb_ctx* c, Slot& s) {
   CK(cudaMemset(s.d_tile_counters, 0, sizeof(int) * 4096));
   CK(cudaMalloc(&s.d_cand_count, sizeof(int) * (size_t)B * C));
   CK(cudaMalloc(&s.d_sel_count, sizeof(int) * (size_t)B * C));
+  CK(cudaMalloc(&s.d_kept_hist, sizeof(int) * (size_t)B * 1024));
   CK(cudaMalloc(&s.d_cand, sizeof(unsigned long long) * (size_t)B * C * N));
   CK(cudaMalloc(&s.d_sel, (sizeof(unsigned long long) + sizeof(int)) * (size_t)B * C * MP));
   CK(cudaMalloc(&s.d_out, sizeof(wb_detection) * (size_t)B * WB_MAX_DETECTIONS));
@@ -250,6 +252,7 @@ int wb_destroy(wb_ctx* c) {
     cudaFree(s.d_tile_counters);
     cudaFree(s.d_cand_count);
     cudaFree(s.d_sel_count);
+    cudaFree(s.d_kept_hist);
     cudaFree(s.d_cand);
     cudaFree(s.d_sel);
     cudaFree(s.d_out);
@@ -473,14 +476,16 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
   return 0;
 }
 
-static int run_post(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t flags) {
+static int run_post(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t flags, bool want_raw = false) {
   LaunchCtx lc{st, &s.launches};
-  float* rb = s.d_raw;
-  float* rs = rb + (size_t)c->max_batch * WB_MAX_DETECTIONS * 4;
-  float* rc = rs + (size_t)c->max_batch * WB_MAX_DETECTIONS;
+  // the float boxes / scores / classes of `sess.run` are a test hook (wb_postprocess); the product path writes
+  // Detection rows only
+  float* rb = want_raw ? s.d_raw : nullptr;
+  float* rs = want_raw ? rb + (size_t)c->max_batch * WB_MAX_DETECTIONS * 4 : nullptr;
+  float* rc = want_raw ? rs + (size_t)c->max_batch * WB_MAX_DETECTIONS : nullptr;
   launch_post(lc, n, c->pp, s.d_enc, s.d_logits, c->tensor(c->hdr.anchors_tensor), s.d_desc, c->d_cams, flags,
               s.d_dec, s.d_cand_count, s.d_cand, s.d_sel_count, s.d_sel, s.d_out, s.d_verdicts, rb, rs, rc,
-              s.d_raw_num);
+              want_raw ? s.d_raw_num : nullptr, s.d_kept_hist);
   CK(cudaGetLastError());
   return 0;
 }
@@ -744,7 +749,7 @@ int wb_postprocess(wb_ctx* c, int n, const float* enc, const float* logits, cons
   CK(cudaMemcpyAsync(s.d_logits, logits, sizeof(float) * (size_t)n * NA * C1, cudaMemcpyHostToDevice, st));
   if (int rc = fill_desc(c, s, n, nullptr, cam_ids, false, st)) return rc;
   s.launches = 0;
-  if (int rc = run_post(c, s, st, n, flags)) return rc;
+  if (int rc = run_post(c, s, st, n, flags, true)) return rc;
   const size_t B = c->max_batch;
   CK(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(wb_detection) * (size_t)n * WB_MAX_DETECTIONS, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(s.h_verdicts, s.d_verdicts, sizeof(uint32_t) * (size_t)n * WB_MAX_DETECTIONS, cudaMemcpyDeviceToHost, st));
