@@ -38,6 +38,7 @@ struct TcArgs {
   // KxK / strided convolutions: the A tile of k-block kb is the tap (kb / cpb) of the filter window, channel block
   // kb % cpb, fetched by a 4-D TMA box {32 ch, OW, OH, imgs} whose traversal strides are the conv stride
   int conv, cpb, conv_kw, conv_pad_t, conv_pad_l;
+  int ring_bytes;     // k_gemm_tc: bytes of the stage ring (re-used as the epilogue's staging tile)
   int rows_per_tile;  // GEMM rows one CTA produces (128, or imgs_per_tile*OH*OW for conv tiles)
   int ta_stages;  // > 0: A operand staged in tensor memory (k_gemm_tc<2, true>), ring of 64-column hi/lo pairs
   int n_main;  // TF32X3: the hi*hi products rotate over n_main TMEM accumulators (+1 for the corrections)
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   static_assert(!TA || X3, "TMEM-staged A exists for the 3xTF32 mode only");
   constexpr int A_SLOTS = TA ? 1 : (X3 ? 2 : 1);  // fp32 tile (+ lo tile when the split stays in smem)
   const int stage_bytes = A_TILE_BYTES * A_SLOTS + b_tile_bytes * (X3 ? 2 : 1);
-  uint8_t* bar_base = smem + (size_t)g.stages * stage_bytes;
+  uint8_t* bar_base = smem + (size_t)g.ring_bytes;  // >= stages * stage_bytes (and >= the epilogue staging tile)
   uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);          // TMA landed
   uint64_t* empty = full + g.stages;                               // MMAs done with the stage
   uint64_t* conv = empty + g.stages;                               // converters done (X3)
@@ -83,9 +84,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   uint64_t* ta_empty = ta_conv + 4;   // [4] TA: MMAs done with a TMEM stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) WB_STAMP(8, 0);  // kernel entry
   const int m0 = blockIdx.x * g.rows_per_tile, n0 = blockIdx.y * g.block_n;
   const int kb0 = blockIdx.z * g.kb_per;
   __shared__ int s_ticket;
+  __shared__ __align__(16) float s_scale[256], s_offset[256];
   const int nkb = min(g.k_blocks, kb0 + g.kb_per) - kb0;  // k-blocks of this split (>= 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
   const int n_acc = X3 ? g.n_main + 1 : 1;
@@ -199,6 +202,13 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = row < g.rows_per_tile && m < g.M;
+    // while the k-loop runs: this tile's folded BN / bias columns -> shared memory
+    for (int j = threadIdx.x - 64; j < g.block_n; j += 128) {
+      const int nn = n0 + j;
+      s_scale[j] = nn < g.n_pad ? __ldg(g.scale + nn) : 1.f;
+      s_offset[j] = nn < g.n_pad ? __ldg(g.offset + nn) : 0.f;
+    }
+    epilogue_bar_sync();
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
     if (threadIdx.x == 64) WB_STAMP(5, 0);
@@ -274,59 +284,59 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         if (threadIdx.x == 64) g.tile_counters[tile_id] = 0;  // ready for the next launch (stream-ordered)
       }
     } else {
-    const int f = g.is_head ? m / g.hw : 0;
-    const size_t head_row = g.is_head ? (size_t)f * g.num_anchors + g.row_off + (size_t)(m - f * g.hw) * g.anchors_per_loc : 0;
+    // Every MMA has completed (acc_full), so the stage ring is dead: it becomes a [128][block_n + 4] fp32 staging
+    // tile.  Phase 1, thread = accumulator row: TMEM -> registers -> folded BN / bias (+ReLU6) -> staging (row pitch
+    // = 4 mod 16 words: the 8 lanes of a store phase hit 8 different bank groups).  Phase 2, warp = 32 rows, lanes
+    // along the columns: 128-byte coalesced stores (the shortcut of a bottleneck `Add` is read the same way).  The
+    // former epilogue stored 64 bytes per thread and row: 32 half-used sectors per instruction.
+    const int pitch = g.block_n + 4;
+    float* stg = reinterpret_cast<float*>(smem);
+    const uint32_t stg_row = smem_u32(stg) + (uint32_t)(row * pitch * 4);
     for (int c0 = 0; c0 < g.block_n; c0 += 16) {
       uint32_t v[16];
       load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
                      min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
-      const int n = n0 + c0;
-      if (!row_ok || n >= g.N) continue;
-      float y[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int nn = n + j;
-        float s = nn < g.n_pad ? __ldg(g.scale + nn) : 1.f, o = nn < g.n_pad ? __ldg(g.offset + nn) : 0.f;
-        float x = affine_rn(__uint_as_float(v[j]), s, o);
-        y[j] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+      for (int j = 0; j < 16; j += 4) {
+        const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
+        float4 y = make_float4(affine_rn(__uint_as_float(v[j]), sc.x, of.x), affine_rn(__uint_as_float(v[j + 1]), sc.y, of.y),
+                               affine_rn(__uint_as_float(v[j + 2]), sc.z, of.z), affine_rn(__uint_as_float(v[j + 3]), sc.w, of.w));
+        if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+        sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
       }
+    }
+    __syncwarp();
+    const int rows = min(g.rows_per_tile, g.M - m0);
+    for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) {
+      const int mm = m0 + r;
+      const uint32_t src = smem_u32(stg) + (uint32_t)(r * pitch * 4);
       if (g.is_head) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int nn = n + j;
+        const int f = mm / g.hw;
+        const size_t hr = (size_t)f * g.num_anchors + g.row_off + (size_t)(mm - f * g.hw) * g.anchors_per_loc;
+        for (int j = lane; j < g.block_n; j += 32) {
+          const int nn = n0 + j;
           if (nn >= g.N) break;
+          const float y = stg[r * pitch + j];
           if (nn < g.n_box)
-            g.enc[head_row * 4 + nn] = y[j];
+            g.enc[hr * 4 + nn] = y;
           else
-            g.logits[head_row * g.ncp1 + (nn - g.n_box)] = y[j];
+            g.logits[hr * g.ncp1 + (nn - g.n_box)] = y;
         }
-      } else if (TF32) {
-        float* o = reinterpret_cast<float*>(g.out) + (size_t)m * g.N + n;
-        const float* rs = g.residual != nullptr ? reinterpret_cast<const float*>(g.residual) + (size_t)m * g.N + n : nullptr;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          if (n + j < g.N) {
-            float4 yy = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-            if (rs != nullptr) {
-              const float4 rr = *reinterpret_cast<const float4*>(rs + j);
-              yy = make_float4(__fadd_rn(yy.x, rr.x), __fadd_rn(yy.y, rr.y), __fadd_rn(yy.z, rr.z), __fadd_rn(yy.w, rr.w));
-            }
-            *reinterpret_cast<float4*>(o + j) = yy;
-          }
       } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)m * g.N + n;
-#pragma unroll
-        for (int j = 0; j < 16; j += 8)
-          if (n + j < g.N) {
-            uint4 pk;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[j], y[j + 1]), p1 = __floats2bfloat162_rn(y[j + 2], y[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[j + 4], y[j + 5]), p3 = __floats2bfloat162_rn(y[j + 6], y[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&p0);
-            pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2);
-            pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(o + j) = pk;
+        for (int j = lane * 4; j < g.block_n; j += 128) {
+          const int nn = n0 + j;
+          if (nn >= g.N) break;
+          float4 y = lds128(src + (uint32_t)(j * 4));
+          if (TF32) {
+            if (g.residual != nullptr) {
+              const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (size_t)mm * g.N + nn);
+              y = make_float4(__fadd_rn(y.x, rr.x), __fadd_rn(y.y, rr.y), __fadd_rn(y.z, rr.z), __fadd_rn(y.w, rr.w));
+            }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)mm * g.N + nn) = y;
+          } else {
+            ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)mm * g.N + nn, y);
           }
+        }
       }
     }
     }
@@ -400,6 +410,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  if (threadIdx.x == 0) WB_STAMP(9, 0);  // kernel exit
 }
 
 
@@ -919,7 +930,12 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   }
   if (stages < 1) stages = 1;
   g.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
+  g.ring_bytes = stages * stage_bytes;
+  if (!persist) {
+    const int staging = BLOCK_M * (g.block_n + 4) * 4;  // epilogue staging tile re-uses the stage ring
+    g.ring_bytes = ((std::max(g.ring_bytes, staging) + 1023) / 1024) * 1024;
+  }
+  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
   alignas(64) CUtensorMap map_a;
   if (g.conv) {
     const int imgs = BLOCK_M / (int)(L.out_h * L.out_w);
