@@ -56,6 +56,76 @@ __device__ __forceinline__ void tma_load_4d_tc(uint32_t dst, const CUtensorMap* 
 // barrier among the four epilogue warps only (128 threads, hardware barrier 1)
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// float4 at shared-memory address `addr` of cluster member `rank` (distributed shared memory)
+__device__ __forceinline__ float4 ld_dsmem128(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
+// One output row of the tile from the staging tile(s) to global memory, lanes along the columns (coalesced).
+// members == 1: the row already carries the layer epilogue.  members > 1 (split-K cluster): the row is the sum of the
+// members' raw partial rows in rank order, then folded BN / bias, ReLU6.  Then the optional bottleneck shortcut, and
+// the store: dense [M][N], or the head scatter into the concatenated box-encoding / class-logit tensors.
+template <bool TF32>
+__device__ __forceinline__ void copy_out_row(const TcArgs& g, const uint8_t* smem, int pitch, int r, int m0, int n0,
+                                             int lane, int members, int reduce) {
+  const int mm = m0 + r;
+  const uint32_t src = smem_u32(smem) + (uint32_t)(r * pitch * 4);
+  size_t hr = 0;
+  if (g.is_head) {
+    const int f = mm / g.hw;
+    hr = (size_t)f * g.num_anchors + g.row_off + (size_t)(mm - f * g.hw) * g.anchors_per_loc;
+  }
+  for (int j = lane * 4; j < g.block_n; j += 128) {
+    const int nn = n0 + j;
+    if (nn >= g.N) break;
+    float4 y;
+    if (reduce) {
+      y = ld_dsmem128(src + (uint32_t)(j * 4), 0);
+      for (int z = 1; z < members; ++z) {
+        const float4 p = ld_dsmem128(src + (uint32_t)(j * 4), (uint32_t)z);
+        y = make_float4(__fadd_rn(y.x, p.x), __fadd_rn(y.y, p.y), __fadd_rn(y.z, p.z), __fadd_rn(y.w, p.w));
+      }
+      const float4 sc = *reinterpret_cast<const float4*>(g.scale + nn), of = *reinterpret_cast<const float4*>(g.offset + nn);
+      y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
+      if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+    } else {
+      y = lds128(src + (uint32_t)(j * 4));
+    }
+    if (g.is_head) {
+      const float ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = nn + e;
+        if (c >= g.N) break;
+        if (c < g.n_box)
+          g.enc[hr * 4 + c] = ys[e];
+        else
+          g.logits[hr * g.ncp1 + (c - g.n_box)] = ys[e];
+      }
+    } else if (TF32) {
+      if (g.residual != nullptr) {
+        const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (size_t)mm * g.N + nn);
+        y = make_float4(__fadd_rn(y.x, rr.x), __fadd_rn(y.y, rr.y), __fadd_rn(y.z, rr.z), __fadd_rn(y.w, rr.w));
+      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)mm * g.N + nn) = y;
+    } else {
+      ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)mm * g.N + nn, y);
+    }
+  }
+}
+
 // MODE 0: bf16 operands; MODE 1: tf32 single product (diagnostic); MODE 2: tf32 x3 split
 // TA (TF32X3 only, experimental, WB_TMEM_A=1): the converter warps write the hi / lo rows into tensor memory
 // (tcgen05.st) and the MMAs take A from there, so the shared-memory port carries neither the converter writes
@@ -87,7 +157,6 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   if (threadIdx.x == 0) WB_STAMP(8, 0);  // kernel entry
   const int m0 = blockIdx.x * g.rows_per_tile, n0 = blockIdx.y * g.block_n;
   const int kb0 = blockIdx.z * g.kb_per;
-  __shared__ int s_ticket;
   __shared__ __align__(16) float s_scale[256], s_offset[256];
   const int nkb = min(g.k_blocks, kb0 + g.kb_per) - kb0;  // k-blocks of this split (>= 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
@@ -212,133 +281,36 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
     if (threadIdx.x == 64) WB_STAMP(5, 0);
-    if (g.splits > 1) {
-      // split-K: raw partial accumulators -> scratch; the LAST CTA to arrive at this output tile adds the partial
-      // tiles in split order (z = 0, 1, ...: the order does not depend on who arrives when, so the result is
-      // deterministic and bit-identical to the former two-kernel reduce) and runs the layer epilogue.
-      for (int c0 = 0; c0 < g.block_n; c0 += 16) {
-        uint32_t v[16];
-        load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
-                       min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
-        const int n = n0 + c0;
-        if (!row_ok || n >= g.n_pad) continue;
-        float* pp = g.partial + ((size_t)blockIdx.z * g.M + m) * g.n_pad + n;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          __stcg(reinterpret_cast<float4*>(pp + j), make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-      }
-      __threadfence();
-      epilogue_bar_sync();
-      const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-      if (threadIdx.x == 64) s_ticket = atomicAdd(&g.tile_counters[tile_id], 1);
-      epilogue_bar_sync();
-      if (s_ticket == g.splits - 1) {
-        __threadfence();
-        const int et = threadIdx.x - 64;  // 0..127
-        const int c4n = g.block_n >> 2;
-        const int rows = min(g.rows_per_tile, g.M - m0);
-        for (int idx = et; idx < rows * c4n; idx += 128) {
-          const int r = idx / c4n, n = n0 + (idx - r * c4n) * 4;
-          if (n >= g.N) continue;
-          const int mm = m0 + r;
-          float4 acc = __ldcg(reinterpret_cast<const float4*>(g.partial + (size_t)mm * g.n_pad + n));
-          for (int z = 1; z < g.splits; ++z) {
-            const float4 p = __ldcg(reinterpret_cast<const float4*>(g.partial + ((size_t)z * g.M + mm) * g.n_pad + n));
-            acc.x = __fadd_rn(acc.x, p.x);
-            acc.y = __fadd_rn(acc.y, p.y);
-            acc.z = __fadd_rn(acc.z, p.z);
-            acc.w = __fadd_rn(acc.w, p.w);
-          }
-          float y[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = affine_rn(y[j], __ldg(g.scale + n + j), __ldg(g.offset + n + j));
-            y[j] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
-          }
-          if (g.is_head) {
-            const int f = mm / g.hw;
-            const size_t hr = (size_t)f * g.num_anchors + g.row_off + (size_t)(mm - f * g.hw) * g.anchors_per_loc;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int nn = n + j;
-              if (nn >= g.N) break;
-              if (nn < g.n_box)
-                g.enc[hr * 4 + nn] = y[j];
-              else
-                g.logits[hr * g.ncp1 + (nn - g.n_box)] = y[j];
-            }
-          } else if (TF32) {
-            if (g.residual != nullptr) {
-              const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (size_t)mm * g.N + n);
-              y[0] = __fadd_rn(y[0], rr.x);
-              y[1] = __fadd_rn(y[1], rr.y);
-              y[2] = __fadd_rn(y[2], rr.z);
-              y[3] = __fadd_rn(y[3], rr.w);
-            }
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)mm * g.N + n) = make_float4(y[0], y[1], y[2], y[3]);
-          } else {
-            ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)mm * g.N + n, make_float4(y[0], y[1], y[2], y[3]));
-          }
-        }
-        if (threadIdx.x == 64) g.tile_counters[tile_id] = 0;  // ready for the next launch (stream-ordered)
-      }
-    } else {
     // Every MMA has completed (acc_full), so the stage ring is dead: it becomes a [128][block_n + 4] fp32 staging
     // tile.  Phase 1, thread = accumulator row: TMEM -> registers -> folded BN / bias (+ReLU6) -> staging (row pitch
-    // = 4 mod 16 words: the 8 lanes of a store phase hit 8 different bank groups).  Phase 2, warp = 32 rows, lanes
-    // along the columns: 128-byte coalesced stores (the shortcut of a bottleneck `Add` is read the same way).  The
-    // former epilogue stored 64 bytes per thread and row: 32 half-used sectors per instruction.
+    // = 4 mod 16 words: the 8 lanes of a store phase hit 8 different bank groups).  Phase 2 (copy_out below), warp =
+    // rows, lanes along the columns: 128-byte coalesced stores.  The former epilogue stored 64 bytes per thread and
+    // row: 32 half-used sectors per instruction.
+    // Split-K: the `splits` CTAs of an output tile form one thread-block cluster; phase 1 stages the RAW partial
+    // accumulators, and after a cluster barrier CTA z reduces rows z, z + splits, ... over all members' staging tiles
+    // through distributed shared memory, always in the order z' = 0, 1, ... (deterministic), then runs the epilogue.
+    const bool raw = g.splits > 1;
     const int pitch = g.block_n + 4;
-    float* stg = reinterpret_cast<float*>(smem);
-    const uint32_t stg_row = smem_u32(stg) + (uint32_t)(row * pitch * 4);
+    const uint32_t stg_row = smem_u32(smem) + (uint32_t)(row * pitch * 4);
     for (int c0 = 0; c0 < g.block_n; c0 += 16) {
       uint32_t v[16];
       load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
                      min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
-        float4 y = make_float4(affine_rn(__uint_as_float(v[j]), sc.x, of.x), affine_rn(__uint_as_float(v[j + 1]), sc.y, of.y),
-                               affine_rn(__uint_as_float(v[j + 2]), sc.z, of.z), affine_rn(__uint_as_float(v[j + 3]), sc.w, of.w));
-        if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+        float4 y = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        if (!raw) {
+          const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
+          y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
+          if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+        }
         sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
       }
     }
     __syncwarp();
-    const int rows = min(g.rows_per_tile, g.M - m0);
-    for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) {
-      const int mm = m0 + r;
-      const uint32_t src = smem_u32(stg) + (uint32_t)(r * pitch * 4);
-      if (g.is_head) {
-        const int f = mm / g.hw;
-        const size_t hr = (size_t)f * g.num_anchors + g.row_off + (size_t)(mm - f * g.hw) * g.anchors_per_loc;
-        for (int j = lane; j < g.block_n; j += 32) {
-          const int nn = n0 + j;
-          if (nn >= g.N) break;
-          const float y = stg[r * pitch + j];
-          if (nn < g.n_box)
-            g.enc[hr * 4 + nn] = y;
-          else
-            g.logits[hr * g.ncp1 + (nn - g.n_box)] = y;
-        }
-      } else {
-        for (int j = lane * 4; j < g.block_n; j += 128) {
-          const int nn = n0 + j;
-          if (nn >= g.N) break;
-          float4 y = lds128(src + (uint32_t)(j * 4));
-          if (TF32) {
-            if (g.residual != nullptr) {
-              const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (size_t)mm * g.N + nn);
-              y = make_float4(__fadd_rn(y.x, rr.x), __fadd_rn(y.y, rr.y), __fadd_rn(y.z, rr.z), __fadd_rn(y.w, rr.w));
-            }
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)mm * g.N + nn) = y;
-          } else {
-            ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)mm * g.N + nn, y);
-          }
-        }
-      }
-    }
+    if (!raw) {
+      const int rows = min(g.rows_per_tile, g.M - m0);
+      for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 0);
     }
     if (threadIdx.x == 64) WB_STAMP(6, 0);
   } else if (X3) {
@@ -404,6 +376,19 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     }
   }
 
+  if (g.splits > 1) {
+    // all `splits` CTAs of this tile (one cluster) have staged their partial tiles
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2 && warp < 6) {
+      const int rows = min(g.rows_per_tile, g.M - m0);
+      const int z = (int)cluster_ctarank();
+      for (int r = z + g.splits * (warp - 2); r < rows; r += 4 * g.splits)
+        copy_out_row<TF32>(g, smem, g.block_n + 4, r, m0, n0, lane, g.splits, 1);
+    }
+    __syncwarp();
+    cluster_sync_all();  // nobody exits while a peer still reads its staging tile
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -873,10 +858,9 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.kb_per = g.k_blocks;
   g.partial = partial;
   const long tiles = (long)grid.x * grid.y;
-  if (partial != nullptr && tile_counters != nullptr && tiles < 74 && tiles <= 4096 && g.k_blocks >= 4) {
+  if (tiles < 74 && g.k_blocks >= 4 && getenv("WB_NO_SPLITK") == nullptr) {
     int want = (int)((148 + tiles - 1) / tiles);  // ~one CTA per SM of a B200
-    int splits = std::min(want, g.k_blocks / 2);
-    while (splits > 1 && (size_t)splits * g.M * g.n_pad > partial_floats) --splits;
+    int splits = std::min(std::min(want, g.k_blocks / 2), 8);  // 8 = portable thread-block cluster size
     if (splits > 1) {
       g.kb_per = (g.k_blocks + splits - 1) / splits;
       g.splits = (g.k_blocks + g.kb_per - 1) / g.kb_per;
@@ -964,6 +948,22 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   }
   static PerDeviceFlag attr_done[6];
   cudaError_t e = cudaSuccess;
+  // split-K launches: the `splits` CTAs of a tile are one thread-block cluster (1, 1, splits)
+  auto launch = [&](auto kern, int threads) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = lc.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = (unsigned)g.splits;
+    cfg.attrs = at;
+    cfg.numAttrs = g.splits > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_b_lo, g);
+  };
   if (persist) {
     CUtensorMap map_out;
     if (!make_out_map(&map_out, out, elem, g.M, g.N, err)) return 1;
@@ -991,29 +991,29 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       e = cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       attr_done[0].set();
     }
-    k_gemm_tc<0><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+    if (e == cudaSuccess) e = launch(k_gemm_tc<0>, 192);
   } else if (mode == TC_TF32X1) {
     if (!attr_done[1].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       attr_done[1].set();
     }
-    k_gemm_tc<1><<<grid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+    if (e == cudaSuccess) e = launch(k_gemm_tc<1>, 192);
   } else if (g.ta_stages > 0) {
     static PerDeviceFlag ta_attr_done;
     if (!ta_attr_done.get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       ta_attr_done.set();
     }
-    k_gemm_tc<2, true><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+    if (e == cudaSuccess) e = launch(k_gemm_tc<2, true>, 320);
   } else {
     if (!attr_done[2].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       attr_done[2].set();
     }
-    k_gemm_tc<2><<<grid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, g);
+    if (e == cudaSuccess) e = launch(k_gemm_tc<2>, 320);
   }
   if (e != cudaSuccess) {
-    *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    *err = std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e);
     return 1;
   }
   ++*lc.launch_counter;
