@@ -48,7 +48,7 @@ def test_two_ranks_shard_scatter_and_reduce():
     procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
+    res = sorted(q.get(timeout=600) for _ in range(world))
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
