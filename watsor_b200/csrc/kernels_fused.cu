@@ -51,7 +51,7 @@ struct FusedArgs {
   int dw_act, act;
   int C, S, pad_t, pad_l;
   int OH, OW, n_img;
-  int N, block_n, k_blocks, n_main;
+  int N, n_pad, block_n, k_blocks, n_main;
   int tiles_x, tiles_y;
   int stages, halo_stages;
   int th_in, tw_in;
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     s_dw[10 * g.C + i] = g.dw_offset[i];
   }
   float* s_pw = s_dw + 11 * g.C;  // [2][block_n]: folded BN of the pointwise output channels
-  for (int i = threadIdx.x; i < g.block_n; i += blockDim.x) {
-    s_pw[i] = g.scale[i];
-    s_pw[g.block_n + i] = g.offset[i];
+  for (int i = threadIdx.x; i < g.block_n; i += blockDim.x) {  // block_n may exceed n_pad (N = 16 / 24: one 32-wide tile)
+    s_pw[i] = i < g.n_pad ? g.scale[i] : 1.f;
+    s_pw[g.block_n + i] = i < g.n_pad ? g.offset[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -344,7 +344,7 @@ struct FusedPlan {
 };
 
 bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
-  p->block_n = pw.n_pad;
+  p->block_n = ((int)pw.n_pad + 31) / 32 * 32;  // weight rows / output columns beyond N: zero-filled / clipped by TMA
   p->n_main = 1;
   p->th_in = (F_TH - 1) * dw.stride + 3;
   p->tw_in = (F_TW - 1) * dw.stride + 3;
@@ -366,13 +366,451 @@ bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
   return false;
 }
 
+
+// ===================================================================================================
+// MobileNet-v2 inverted residual block as ONE kernel (`expanded_conv_k/{expand,depthwise,project}` [+ `add`] of the
+// TF-slim graph a SSD-MobileNet-v2 frozen_inference_graph.pb holds; ref: watsor/detection/tensorflow_cpu.py:114 runs
+// them inside sess.run):
+//     1x1 expand (C_in <= 32 -> C, BN, ReLU6)  ->  depthwise 3x3 stride S (BN, ReLU6)  ->  1x1 linear projection
+//     (C -> N <= 128, BN)  [-> + shortcut]
+// The 6x expanded tensor (69 MB per batch of 8 at 150x150x96) and the depthwise output never leave the SM.
+//
+// Persistent kernel, output tile = 8 x 16 pixels.  Per tile the TMA warp fetches the INPUT halo tile
+// ((7S+3) x (15S+3) pixels x C_in, out-of-image pixels zero-filled).  Then, per 32-channel block of the expanded
+// tensor:
+//   warps 16..23  expand producers: fp32 FFMA on CUDA cores (K = C_in is 16 .. 32: a tensor-core pass would need the
+//                 halo tile as a second swizzled hi/lo operand in shared memory, which does not fit beside the rest),
+//                 BN + ReLU6, zero outside the image (= the depthwise conv's SAME padding), written as the
+//                 depthwise halo chunk [pixels][32 ch]
+//   warps 8..15   depthwise producers: 3x3 window from the halo chunk, BN + ReLU6, TF32 hi/lo split, written
+//                 straight into the 128B-swizzled UMMA A tiles (same code path as k_dwpw_tc_x3, any stride)
+//   warp 5        tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
+//   warps 0..3    epilogue: tcgen05.ld -> BN (+ shortcut read from the block input) -> swizzled staging -> TMA store
+//   warp 4        TMA producer (input halo tiles, projection weight tiles hi / lo)
+struct IrbArgs {
+  const float* we;  // expand weights [C_in][we_ld]
+  const float* e_scale;
+  const float* e_offset;
+  const float* dw_w;  // [9][C]
+  const float* dw_scale;
+  const float* dw_offset;
+  const float* scale;  // projection, [n_pad]
+  const float* offset;
+  const float* residual;  // block input [n][IH][IW][C_in] when the bottleneck Add is fused (C_in == N), else NULL
+  int we_ld, e_act, dw_act, act;
+  int Cin, C, Cr;  // Cr = C rounded up to 32
+  int IH, IW, pad_t, pad_l, OH, OW, n_img;
+  int N, n_pad, block_n, k_blocks, n_main;
+  int tiles_x, tiles_y, stages, halo_stages, in_stages, th_in, tw_in;
+};
+
+constexpr int IRB_EXPAND_WARPS = 8;
+constexpr int IRB_FIRST_EXPAND_THREAD = F_THREADS;                    // 512
+constexpr int IRB_THREADS = F_THREADS + 32 * IRB_EXPAND_WARPS;        // 768
+
+template <int S>
+__global__ void __launch_bounds__(IRB_THREADS, 1)
+    k_irb_x3(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+             const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out, IrbArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int P = g.th_in * g.tw_in;  // halo pixels
+  const int in_bytes = ((P * g.Cin * 4 + 1023) / 1024) * 1024;
+  const int halo_bytes = ((P * ROW_BYTES + 1023) / 1024) * 1024;
+  const int b_tile_bytes = g.block_n * ROW_BYTES;
+  const int ab_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  uint8_t* in0 = smem;
+  uint8_t* halo0 = in0 + (size_t)g.in_stages * in_bytes;
+  uint8_t* ab0 = halo0 + (size_t)g.halo_stages * halo_bytes;
+  uint8_t* staging = ab0 + (size_t)g.stages * ab_bytes;
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(staging + F_STAGING_BYTES);
+  uint64_t* in_empty = in_full + 2;
+  uint64_t* halo_full = in_empty + 2;
+  uint64_t* halo_empty = halo_full + g.halo_stages;
+  uint64_t* b_full = halo_empty + g.halo_stages;
+  uint64_t* a_ready = b_full + g.stages;
+  uint64_t* empty = a_ready + g.stages;
+  uint64_t* acc_full = empty + g.stages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_dw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [11][Cr]
+  float* s_pw = s_dw + 11 * g.Cr;      // [2][block_n]
+  float* s_e = s_pw + 2 * g.block_n;   // [2][Cr]: folded BN of the expand layer
+  float* s_we = s_e + 2 * g.Cr;        // [Cin][Cr]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int num_tiles = tiles_per_img * g.n_img;
+  const int n_acc = g.n_main + 1;
+  const int set_cols = n_acc * g.block_n;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * set_cols) tmem_cols <<= 1;
+
+  if (warp == 4 && lane == 0) {
+    for (int i = 0; i < g.in_stages; ++i) {
+      mbar_init(smem_u32(&in_full[i]), 1);
+      mbar_init(smem_u32(&in_empty[i]), IRB_EXPAND_WARPS);
+    }
+    for (int h = 0; h < g.halo_stages; ++h) {
+      mbar_init(smem_u32(&halo_full[h]), IRB_EXPAND_WARPS);
+      mbar_init(smem_u32(&halo_empty[h]), F_PRODUCER_WARPS);
+    }
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&a_ready[s]), F_PRODUCER_WARPS);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  // per-channel tables; channels C .. Cr-1 (the ragged last 32-block, e.g. C = 144) are zero: they expand to 0,
+  // convolve to 0 and meet zero-filled projection weights
+  for (int i = threadIdx.x; i < 11 * g.Cr; i += blockDim.x) {
+    const int k = i / g.Cr, c = i - k * g.Cr;
+    float v = 0.f;
+    if (c < g.C) v = k < 9 ? g.dw_w[k * g.C + c] : (k == 9 ? g.dw_scale[c] : g.dw_offset[c]);
+    s_dw[i] = v;
+  }
+  for (int i = threadIdx.x; i < g.block_n; i += blockDim.x) {
+    s_pw[i] = i < g.n_pad ? g.scale[i] : 1.f;
+    s_pw[g.block_n + i] = i < g.n_pad ? g.offset[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < g.Cr; i += blockDim.x) {
+    s_e[i] = i < g.C ? g.e_scale[i] : 0.f;
+    s_e[g.Cr + i] = i < g.C ? g.e_offset[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < g.Cin * g.Cr; i += blockDim.x) {
+    const int k = i / g.Cr, c = i - k * g.Cr;
+    s_we[i] = c < g.C ? g.we[(size_t)k * g.we_ld + c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int it = 0, j = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+        const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+        const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
+        const int ib = j % g.in_stages;
+        mbar_wait(smem_u32(&in_empty[ib]), ((j / g.in_stages) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&in_full[ib]);
+        mbar_expect_tx(fb, (uint32_t)(P * g.Cin * 4));
+        tma_load_4d(smem_u32(in0 + (size_t)ib * in_bytes), &map_in, fb, 0, ox0 * S - g.pad_l, oy0 * S - g.pad_t, img);
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const int s = it % g.stages;
+          mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
+          const uint32_t bb = smem_u32(&b_full[s]);
+          uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;
+          mbar_expect_tx(bb, 2 * b_tile_bytes);
+          tma_load_2d(smem_u32(sb), &map_b, bb, kb * 32, 0);
+          tma_load_2d(smem_u32(sb + b_tile_bytes), &map_b_lo, bb, kb * 32, 0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(true, BLOCK_M, g.block_n);
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * set_cols);
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
+        mbar_wait(smem_u32(&a_ready[s]), ph);
+        mbar_wait(smem_u32(&b_full[s]), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          uint8_t* st = ab0 + (size_t)s * ab_bytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+            const uint32_t koff = k * UMMA_K_BYTES;
+            const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+            const uint32_t d_main = acc0 + (uint32_t)((step % g.n_main) * g.block_n);
+            const uint32_t d_corr = acc0 + (uint32_t)(g.n_main * g.block_n);
+            umma<true>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
+            umma<true>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
+            umma<true>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty[s]));
+          if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    uint8_t* my_stage = staging + (size_t)q * 2 * 4096;
+    const int used = min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES));
+    int j = 0, chunk_no = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+      const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
+      mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
+      // this thread's output pixel (row q*32 + lane of the tile = spatial row 2q + lane/16, column lane%16)
+      const int oy = oy0 + 2 * q + (lane >> 4), ox = ox0 + (lane & 15);
+      const bool px_ok = oy < g.OH && ox < g.OW;
+      for (int c0 = 0; c0 < g.block_n; c0 += 32, ++chunk_no) {
+        float y[32];
+        {
+          uint32_t v[32];
+          load_acc32<true>(acc0 + (uint32_t)c0, g.block_n, g.n_main, used, v);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const int nn = c0 + i4 * 4;
+            const float4 sc = lds128(smem_u32(s_pw + nn)), of = lds128(smem_u32(s_pw + g.block_n + nn));
+            const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, ofs[4] = {of.x, of.y, of.z, of.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = affine_rn(__uint_as_float(v[i4 * 4 + e]), scs[e], ofs[e]);
+              y[i4 * 4 + e] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+            }
+          }
+        }
+        if (g.residual != nullptr && px_ok) {
+          // bottleneck `Add`: shortcut = the block input at the same pixel (stride 1, C_in == N)
+          const float* rs = g.residual + (((size_t)img * g.IH + oy) * g.IW + ox) * g.Cin + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c0 + i < g.N) {
+              const float4 rr = *reinterpret_cast<const float4*>(rs + i);
+              y[i + 0] = __fadd_rn(y[i + 0], rr.x);
+              y[i + 1] = __fadd_rn(y[i + 1], rr.y);
+              y[i + 2] = __fadd_rn(y[i + 2], rr.z);
+              y[i + 3] = __fadd_rn(y[i + 3], rr.w);
+            }
+        }
+        if (chunk_no >= 2) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        const uint32_t sb = smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096 + (size_t)lane * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 pk;
+          pk.x = __float_as_uint(y[c * 4 + 0]);
+          pk.y = __float_as_uint(y[c * 4 + 1]);
+          pk.z = __float_as_uint(y[c * 4 + 2]);
+          pk.w = __float_as_uint(y[c * 4 + 3]);
+          sts128(sb + (uint32_t)((c ^ (lane & 7)) << 4), pk);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          // columns >= N and pixels outside the map are clipped by the tensor map
+          tma_store_4d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), c0, ox0, oy0 + 2 * q, img);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  } else if (warp >= 8 && warp < 16) {
+    // ------------------------------------------------------------------ depthwise producers
+    const int pt = threadIdx.x - F_FIRST_PRODUCER_THREAD;
+    const int q = pt & 7, slot = pt >> 3;  // channel quad of the k-block, pixel slot
+    constexpr int NCOL = 3 * S + 3;        // input columns feeding 4 adjacent outputs
+    const int TW_IN = g.tw_in;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int h = it % g.halo_stages, s = it % g.stages;
+        const int cch = kb * 32 + q * 4;
+        float4 wr[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wr[k] = lds128(smem_u32(s_dw + k * g.Cr + cch));
+        const float4 sc = lds128(smem_u32(s_dw + 9 * g.Cr + cch));
+        const float4 of = lds128(smem_u32(s_dw + 10 * g.Cr + cch));
+        mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
+        mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
+        const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
+        const uint32_t a_hi = smem_u32(ab0 + (size_t)s * ab_bytes);
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const int ty = slot >> 2, x0 = (slot & 3) * 4;
+        const uint32_t win = hal + (uint32_t)(((ty * S) * TW_IN + x0 * S) * 128 + q * 16);
+        float4 acc[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) {
+            const float4 x = lds128(win + (uint32_t)((ky * TW_IN + c) * 128));
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // output o reads input column o*S + kx; accumulation order (ky, kx) as in k_dw_strip
+              if ((c - kx) >= 0 && (c - kx) % S == 0 && (c - kx) / S < 4) {
+                const int o = (c - kx) / S;
+                const float4 ww = wr[ky * 3 + kx];
+                acc[o].x = fmaf(x.x, ww.x, acc[o].x);
+                acc[o].y = fmaf(x.y, ww.y, acc[o].y);
+                acc[o].z = fmaf(x.z, ww.z, acc[o].z);
+                acc[o].w = fmaf(x.w, ww.w, acc[o].w);
+              }
+            }
+          }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int r = ty * F_TW + x0 + o;
+          float v[4] = {affine_rn(acc[o].x, sc.x, of.x), affine_rn(acc[o].y, sc.y, of.y),
+                        affine_rn(acc[o].z, sc.z, of.z), affine_rn(acc[o].w, sc.w, of.w)};
+          uint4 hi, lo;
+          uint32_t* hp = &hi.x;
+          uint32_t* lp = &lo.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = g.dw_act == WB_ACT_RELU6 ? relu6f(v[e]) : v[e];
+            const uint32_t hb = __float_as_uint(a) & 0xFFFFE000u;
+            hp[e] = hb;
+            lp[e] = __float_as_uint(__fsub_rn(a, __uint_as_float(hb))) & 0xFFFFE000u;
+          }
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);  // 128B swizzle
+          sts128(a_hi + off, hi);
+          sts128(a_lo + off, lo);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&a_ready[s]));
+          mbar_arrive(smem_u32(&halo_empty[h]));
+        }
+      }
+    }
+  } else if (warp >= 16) {
+    // ------------------------------------------------------------------ expand producers (CUDA cores, fp32)
+    const int et = threadIdx.x - IRB_FIRST_EXPAND_THREAD;  // 0..255
+    const int q = et & 7, g0 = et >> 3;                    // channel quad of the k-block; first pixel group
+    const int groups = (P + 3) >> 2;
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
+      const int img_r = t % tiles_per_img;
+      const int iy0 = (img_r / g.tiles_x) * F_TH * S - g.pad_t, ix0 = (img_r % g.tiles_x) * F_TW * S - g.pad_l;
+      const int ib = j % g.in_stages;
+      mbar_wait(smem_u32(&in_full[ib]), (j / g.in_stages) & 1);
+      const uint32_t tin = smem_u32(in0 + (size_t)ib * in_bytes);
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const int h = it % g.halo_stages;
+        mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
+        const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
+        const int cch = kb * 32 + q * 4;
+        const float4 sc = lds128(smem_u32(s_e + cch)), of = lds128(smem_u32(s_e + g.Cr + cch));
+        const uint32_t wbase = smem_u32(s_we + cch);
+        for (int gr = g0; gr < groups; gr += 32) {
+          const int p0 = gr * 4;
+          float4 acc[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c4 = 0; c4 < g.Cin; c4 += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = lds128(wbase + (uint32_t)((c4 + e) * g.Cr * 4));
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int p = min(p0 + o, P - 1);
+              const float4 x = lds128(tin + (uint32_t)((p * g.Cin + c4) * 4));
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[o].x = fmaf(xs[e], w[e].x, acc[o].x);
+                acc[o].y = fmaf(xs[e], w[e].y, acc[o].y);
+                acc[o].z = fmaf(xs[e], w[e].z, acc[o].z);
+                acc[o].w = fmaf(xs[e], w[e].w, acc[o].w);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int p = p0 + o;
+            if (p >= P) break;
+            const int ly = p / g.tw_in, lx = p - ly * g.tw_in;
+            const int iy = iy0 + ly, ix = ix0 + lx;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the map: the depthwise conv's zero padding
+            if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
+              y = make_float4(affine_rn(acc[o].x, sc.x, of.x), affine_rn(acc[o].y, sc.y, of.y),
+                              affine_rn(acc[o].z, sc.z, of.z), affine_rn(acc[o].w, sc.w, of.w));
+              if (g.e_act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+            }
+            sts128(hal + (uint32_t)(p * 128 + q * 16),
+                   make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&halo_full[h]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&in_empty[ib]));  // the input tile may be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+struct IrbPlan {
+  int block_n, n_main, stages, halo_stages, in_stages, th_in, tw_in, tiles_x, tiles_y, Cr, k_blocks;
+  size_t smem;
+};
+
+bool make_irb_plan(const wb_layer& ex, const wb_layer& dw, const wb_layer& pw, IrbPlan* p) {
+  p->block_n = ((int)pw.n_pad + 31) / 32 * 32;
+  p->Cr = ((int)dw.out_c + 31) / 32 * 32;
+  p->k_blocks = p->Cr / 32;
+  p->n_main = p->k_blocks * 4 <= 32 ? 1 : 2;  // accumulation chains longer than 32 MMAs rotate over two accumulators
+  p->th_in = (F_TH - 1) * dw.stride + 3;
+  p->tw_in = (F_TW - 1) * dw.stride + 3;
+  p->tiles_x = (dw.out_w + F_TW - 1) / F_TW;
+  p->tiles_y = (dw.out_h + F_TH - 1) / F_TH;
+  if (2 * (p->n_main + 1) * p->block_n > 512) return false;
+  const size_t P = (size_t)p->th_in * p->tw_in;
+  const size_t in_b = (P * ex.in_c * 4 + 1023) / 1024 * 1024;
+  const size_t halo = (P * ROW_BYTES + 1023) / 1024 * 1024;
+  const size_t ab = 2 * A_TILE_BYTES + 2 * (size_t)p->block_n * ROW_BYTES;
+  const size_t tables = 4 * ((size_t)11 * p->Cr + 2 * p->block_n + 2 * p->Cr + (size_t)ex.in_c * p->Cr) + 64;
+  const size_t fixed = F_STAGING_BYTES + 1024 + 8 * 32 + tables;
+  const size_t budget = 227 * 1024;
+  // preference: two A/B stages and two halo chunks (overlap of expand / depthwise / MMA), then a second input tile
+  const int opts[5][3] = {{2, 2, 2}, {2, 2, 1}, {1, 2, 1}, {2, 1, 1}, {1, 1, 1}};  // {stages, halo_stages, in_stages}
+  for (auto& o : opts) {
+    const size_t need = o[2] * in_b + o[1] * halo + o[0] * ab + fixed;
+    if (need <= budget) {
+      p->stages = o[0];
+      p->halo_stages = o[1];
+      p->in_stages = o[2];
+      p->smem = need;
+      return true;
+    }
+  }
+  return false;
+}
 }  // namespace
 
 bool fused_dwpw_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& dw, const wb_layer& pw, int n) {
   if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr) return false;
   if (dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
   if (dw.kh != 3 || dw.kw != 3 || dw.stride != 1) return false;  // stride 2: the 17x33 halo does not fit beside the fp32 rings
-  if (dw.out_c % 32 != 0 || pw.in_c != dw.out_c || pw.out_c != pw.n_pad || pw.n_pad > 128 || pw.n_pad % 32 != 0) return false;
+  if (dw.out_c % 32 != 0 || pw.in_c != dw.out_c || pw.n_pad > 128 || pw.out_c % 4 != 0) return false;
   if (pw.in_c > 256) return false;  // one main accumulator: keep the accumulation chain short
   {  // the fused kernel reads the depthwise input while it writes the 1x1 output: they must not overlap
     const unsigned long long a0 = dw.in_off, a1 = a0 + (unsigned long long)dw.in_h * dw.in_w * dw.in_c;
@@ -411,6 +849,7 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
   g.OW = dw.out_w;
   g.n_img = n;
   g.N = pw.out_c;
+  g.n_pad = pw.n_pad;
   g.block_n = p.block_n;
   g.k_blocks = (dw.out_c + 31) / 32;
   g.n_main = p.n_main;
@@ -465,6 +904,130 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
   ++*lc.launch_counter;
   return 0;
 }
+
+// expand (1x1, ReLU6) -> depthwise 3x3 -> linear 1x1 projection [-> Add]: can the three (four) layers run as k_irb_x3?
+bool fused_irb_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& ex, const wb_layer& dw, const wb_layer& pw,
+                         const wb_layer* add, int n) {
+  if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr || getenv("WB_NO_IRB") != nullptr) return false;
+  if (ex.op != WB_OP_PW || dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
+  if (dw.in_off != ex.out_off || pw.in_off != dw.out_off) return false;
+  if (ex.in_c > 32 || ex.in_c % 4 != 0 || (ex.in_c * 4) % 16 != 0) return false;  // CUDA-core expand: small K only
+  if (dw.kh != 3 || dw.kw != 3 || (dw.stride != 1 && dw.stride != 2)) return false;
+  if (dw.out_c % 16 != 0 || ex.out_c != dw.out_c || pw.in_c != dw.out_c || pw.n_pad > 128 || pw.out_c % 4 != 0) return false;
+  if (!tw.layers[pw_layer_index].ready) return false;
+  IrbPlan p;
+  if (!make_irb_plan(ex, dw, pw, &p)) return false;
+  const unsigned long long a0 = ex.in_off, a1 = a0 + (unsigned long long)ex.in_h * ex.in_w * ex.in_c;
+  const wb_layer& last = add ? *add : pw;
+  const unsigned long long b0 = last.out_off, b1 = b0 + (unsigned long long)last.out_h * last.out_w * last.out_c;
+  if (a0 < b1 && b0 < a1) return false;  // the kernel reads the block input while it writes the block output
+  if (add) {
+    if (add->op != WB_OP_ADD || dw.stride != 1 || ex.in_c != pw.out_c) return false;
+    const bool a_is_pw = add->in_off == pw.out_off, b_is_pw = add->in2_off == pw.out_off;
+    const uint32_t other = a_is_pw ? add->in2_off : add->in_off;
+    if (!(a_is_pw || b_is_pw) || other != ex.in_off) return false;
+  }
+  // worth it only when the tile list keeps most SMs busy
+  return (long)p.tiles_x * p.tiles_y * n >= 96;
+}
+
+int fused_launch_irb(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_index, int n, const wb_layer& ex,
+                     const wb_layer& dw, const wb_layer& pw, bool with_add, const void* in, const float* ex_w,
+                     const float* ex_scale, const float* ex_offset, const float* dw_w, const float* dw_scale,
+                     const float* dw_offset, const float* scale, const float* offset, void* out, std::string* err) {
+  const TcLayerWeights& w = tw.layers[pw_layer_index];
+  IrbPlan p;
+  if (!make_irb_plan(ex, dw, pw, &p)) {
+    *err = "fused inverted residual block: no shared-memory plan";
+    return 1;
+  }
+  IrbArgs g;
+  g.we = ex_w;
+  g.we_ld = ex.n_pad;
+  g.e_scale = ex_scale;
+  g.e_offset = ex_offset;
+  g.dw_w = dw_w;
+  g.dw_scale = dw_scale;
+  g.dw_offset = dw_offset;
+  g.scale = scale;
+  g.offset = offset;
+  g.residual = with_add ? static_cast<const float*>(in) : nullptr;
+  g.e_act = ex.act;
+  g.dw_act = dw.act;
+  g.act = pw.act;
+  g.Cin = ex.in_c;
+  g.C = dw.out_c;
+  g.Cr = p.Cr;
+  g.IH = dw.in_h;
+  g.IW = dw.in_w;
+  g.pad_t = dw.pad_t;
+  g.pad_l = dw.pad_l;
+  g.OH = dw.out_h;
+  g.OW = dw.out_w;
+  g.n_img = n;
+  g.N = pw.out_c;
+  g.n_pad = pw.n_pad;
+  g.block_n = p.block_n;
+  g.k_blocks = p.k_blocks;
+  g.n_main = p.n_main;
+  g.tiles_x = p.tiles_x;
+  g.tiles_y = p.tiles_y;
+  g.stages = p.stages;
+  g.halo_stages = p.halo_stages;
+  g.in_stages = p.in_stages;
+  g.th_in = p.th_in;
+  g.tw_in = p.tw_in;
+  alignas(64) CUtensorMap map_in, map_out, map_b, map_b_lo;
+  {
+    unsigned long long dims[4] = {(unsigned long long)ex.in_c, ex.in_w, ex.in_h, (unsigned long long)n};
+    unsigned long long st[3] = {(unsigned long long)ex.in_c * 4, (unsigned long long)ex.in_w * ex.in_c * 4,
+                                (unsigned long long)ex.in_h * ex.in_w * ex.in_c * 4};
+    unsigned box[4] = {(unsigned)ex.in_c, (unsigned)p.tw_in, (unsigned)p.th_in, 1};
+    if (!tc_encode_map(&map_in, in, 4, 4, dims, st, box, false, err)) return 1;
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)pw.out_c, pw.out_w, pw.out_h, (unsigned long long)n};
+    unsigned long long st[3] = {(unsigned long long)pw.out_c * 4, (unsigned long long)pw.out_w * pw.out_c * 4,
+                                (unsigned long long)pw.out_h * pw.out_w * pw.out_c * 4};
+    unsigned box[4] = {32, F_TW, 2, 1};
+    if (!tc_encode_map(&map_out, out, 4, 4, dims, st, box, true, err)) return 1;
+  }
+  {
+    unsigned long long dims[2] = {(unsigned long long)w.k, (unsigned long long)w.n_pad};
+    unsigned long long st[1] = {(unsigned long long)w.k * 4};
+    unsigned box[2] = {32, (unsigned)p.block_n};
+    if (!tc_encode_map(&map_b, w.w, 4, 2, dims, st, box, true, err)) return 1;
+    if (!tc_encode_map(&map_b_lo, w.w_lo, 4, 2, dims, st, box, true, err)) return 1;
+  }
+  static PerDeviceFlag attr_done;
+  if (!attr_done.get()) {
+    cudaError_t e = cudaFuncSetAttribute(k_irb_x3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_irb_x3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+      return 1;
+    }
+    attr_done.set();
+  }
+  static int ctas = 0;
+  if (ctas == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("WB_PERSIST_CTAS");
+    ctas = e ? atoi(e) : sms;
+    if (ctas <= 0 || ctas > sms) ctas = sms;
+  }
+  const long tiles = (long)p.tiles_x * p.tiles_y * n;
+  const dim3 grid((unsigned)std::min<long>(tiles, ctas));
+  if (dw.stride == 1)
+    k_irb_x3<1><<<grid, IRB_THREADS, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
+  else
+    k_irb_x3<2><<<grid, IRB_THREADS, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
+  ++*lc.launch_counter;
+  return 0;
+}
+
 
 #ifdef WB_TRACE
 extern "C" int wb_trace_read_fused(long long* dst) {

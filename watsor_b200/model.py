@@ -133,6 +133,17 @@ class Model:
             nxt = self.layers[i + 1]
             if l.op == OP_PW and nxt.op == OP_ADD and l.dst in (nxt.src, nxt.src2) and l.src:
                 last_use[l.src] = max(last_use[l.src], i + 1)
+        # an inverted residual block (1x1 expand -> depthwise -> linear 1x1 projection [-> Add]) may run as ONE kernel
+        # (csrc/kernels_fused.cu k_irb_x3) that reads the block INPUT while it writes the block OUTPUT: the input must
+        # outlive the block's last layer
+        for i, l in enumerate(self.layers[:-2]):
+            d, p_ = self.layers[i + 1], self.layers[i + 2]
+            if l.op == OP_PW and d.op == OP_DW and p_.op == OP_PW and d.src == l.dst and p_.src == d.dst and l.src:
+                end_ = i + 2
+                if i + 3 < len(self.layers) and self.layers[i + 3].op == OP_ADD and \
+                        p_.dst in (self.layers[i + 3].src, self.layers[i + 3].src2):
+                    end_ = i + 3
+                last_use[l.src] = max(last_use[l.src], end_)
         size = {}
         for l in self.layers:
             if l.dst:
