@@ -23,8 +23,8 @@ def dump(e, n_it):
     assert e.lib.wb_trace_read_gemm(buf) == 0
     t = np.array(buf, dtype=np.int64).reshape(SLOTS, ITERS)
     t0 = t[8, 0]
-    print('   entry 0   setup %d   epi_start %d   epi_done %d   exit %d   (cycles @1.965 GHz; %.2f us total)'
-          % (t[7, 0] - t0, t[5, 0] - t0, t[6, 0] - t0, t[9, 0] - t0, (t[9, 0] - t0) / 1965.0))
+    print('   entry 0   setup %d   epi_start %d   staged %d   epi_done %d   cluster_synced %d   exit %d   (cycles @1.965 GHz; %.2f us total)'
+          % (t[7, 0] - t0, t[5, 0] - t0, t[10, 0] - t0, t[6, 0] - t0, t[11, 0] - t0, t[9, 0] - t0, (t[9, 0] - t0) / 1965.0))
     print('   %-4s' % 'it' + ''.join('%11s' % GEMM[k] for k in sorted(GEMM)))
     for it in range(n_it):
         print('   %-4d' % it + ''.join('%11d' % (t[k, it] - t0) for k in sorted(GEMM)))

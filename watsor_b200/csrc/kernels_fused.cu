@@ -378,12 +378,12 @@ bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
 // Persistent kernel, output tile = 8 x 16 pixels.  Per tile the TMA warp fetches the INPUT halo tile
 // ((7S+3) x (15S+3) pixels x C_in, out-of-image pixels zero-filled).  Then, per 32-channel block of the expanded
 // tensor:
-//   warps 16..23  expand producers: fp32 FFMA on CUDA cores (K = C_in is 16 .. 32: a tensor-core pass would need the
+//   warps 14..21  expand producers: fp32 FFMA on CUDA cores (K = C_in is 16 .. 32: a tensor-core pass would need the
 //                 halo tile as a second swizzled hi/lo operand in shared memory, which does not fit beside the rest),
 //                 BN + ReLU6, zero outside the image (= the depthwise conv's SAME padding), written as the
 //                 depthwise halo chunk [pixels][32 ch]
-//   warps 8..15   depthwise producers: 3x3 window from the halo chunk, BN + ReLU6, TF32 hi/lo split, written
-//                 straight into the 128B-swizzled UMMA A tiles (same code path as k_dwpw_tc_x3, any stride)
+//   warps 6..13   depthwise producers: 3x3 window from the halo chunk, BN + ReLU6, TF32 hi/lo split, written
+//                 straight into the 128B-swizzled UMMA A tiles (same arithmetic as k_dwpw_tc_x3, stride 1 or 2)
 //   warp 5        tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
 //   warps 0..3    epilogue: tcgen05.ld -> BN (+ shortcut read from the block input) -> swizzled staging -> TMA store
 //   warp 4        TMA producer (input halo tiles, projection weight tiles hi / lo)
@@ -405,8 +405,9 @@ struct IrbArgs {
 };
 
 constexpr int IRB_EXPAND_WARPS = 8;
-constexpr int IRB_FIRST_EXPAND_THREAD = F_THREADS;                    // 512
-constexpr int IRB_THREADS = F_THREADS + 32 * IRB_EXPAND_WARPS;        // 768
+constexpr int IRB_FIRST_DW_THREAD = 192;                                             // warps 6..13
+constexpr int IRB_FIRST_EXPAND_THREAD = IRB_FIRST_DW_THREAD + 32 * F_PRODUCER_WARPS;  // warps 14..21
+constexpr int IRB_THREADS = IRB_FIRST_EXPAND_THREAD + 32 * IRB_EXPAND_WARPS;          // 704
 
 template <int S>
 __global__ void __launch_bounds__(IRB_THREADS, 1)
@@ -623,9 +624,9 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
     }
     if (lane == 0) bulk_wait_read<0>();
-  } else if (warp >= 8 && warp < 16) {
+  } else if (warp >= 6 && warp < 14) {
     // ------------------------------------------------------------------ depthwise producers
-    const int pt = threadIdx.x - F_FIRST_PRODUCER_THREAD;
+    const int pt = threadIdx.x - IRB_FIRST_DW_THREAD;
     const int q = pt & 7, slot = pt >> 3;  // channel quad of the k-block, pixel slot
     constexpr int NCOL = 3 * S + 3;        // input columns feeding 4 adjacent outputs
     const int TW_IN = g.tw_in;
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         const uint32_t a_hi = smem_u32(ab0 + (size_t)s * ab_bytes);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
         const int ty = slot >> 2, x0 = (slot & 3) * 4;
-        const uint32_t win = hal + (uint32_t)(((ty * S) * TW_IN + x0 * S) * 128 + q * 16);
+        const int p00 = (ty * S) * TW_IN + x0 * S;  // halo pixel of the window's top-left corner
         float4 acc[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -653,7 +654,8 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int c = 0; c < NCOL; ++c) {
-            const float4 x = lds128(win + (uint32_t)((ky * TW_IN + c) * 128));
+            const int hp = p00 + ky * TW_IN + c;  // halo rows are 128 B, 16-byte chunks XOR-swizzled by pixel % 8
+            const float4 x = lds128(hal + (uint32_t)(hp * 128 + ((q ^ (hp & 7)) << 4)));
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               // output o reads input column o*S + kx; accumulation order (ky, kx) as in k_dw_strip
@@ -694,11 +696,13 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         }
       }
     }
-  } else if (warp >= 16) {
+  } else if (warp >= 14) {
     // ------------------------------------------------------------------ expand producers (CUDA cores, fp32)
-    const int et = threadIdx.x - IRB_FIRST_EXPAND_THREAD;  // 0..255
-    const int q = et & 7, g0 = et >> 3;                    // channel quad of the k-block; first pixel group
-    const int groups = (P + 3) >> 2;
+    // warp-item = 64 consecutive halo pixels x 16 channels of the k-block: lane = pixel (two pixels per thread, 32
+    // apart), so the pixel loads are conflict-free 16-byte accesses and every weight vector (one broadcast LDS.128) feeds
+    // 8 FMAs.  Per c: acc += x[c] * w[c][:] in ascending c, fp32 FFMA (the same arithmetic as the CUDA-core GEMM).
+    const int ew = warp - 14;
+    const int n_items = ((P + 63) >> 6) * 2;
     int it = 0, j = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
       const int img_r = t % tiles_per_img;
@@ -710,46 +714,55 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         const int h = it % g.halo_stages;
         mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
         const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
-        const int cch = kb * 32 + q * 4;
-        const float4 sc = lds128(smem_u32(s_e + cch)), of = lds128(smem_u32(s_e + g.Cr + cch));
-        const uint32_t wbase = smem_u32(s_we + cch);
-        for (int gr = g0; gr < groups; gr += 32) {
-          const int p0 = gr * 4;
-          float4 acc[4];
+        for (int item = ew; item < n_items; item += IRB_EXPAND_WARPS) {
+          const int half = item & 1, pbase = (item >> 1) * 64;
+          const int cch = kb * 32 + half * 16;
+          const int pa = pbase + lane, pb = pbase + 32 + lane;
+          const uint32_t xa = tin + (uint32_t)(min(pa, P - 1) * g.Cin * 4), xb = tin + (uint32_t)(min(pb, P - 1) * g.Cin * 4);
+          const uint32_t wbase = smem_u32(s_we + cch);
+          float acc_a[16], acc_b[16];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 16; ++i) acc_a[i] = acc_b[i] = 0.f;
           for (int c4 = 0; c4 < g.Cin; c4 += 4) {
-            float4 w[4];
+            const float4 va = lds128(xa + (uint32_t)(c4 * 4)), vb = lds128(xb + (uint32_t)(c4 * 4));
+            const float a4[4] = {va.x, va.y, va.z, va.w}, b4[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = lds128(wbase + (uint32_t)((c4 + e) * g.Cr * 4));
+            for (int e = 0; e < 4; ++e) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const int p = min(p0 + o, P - 1);
-              const float4 x = lds128(tin + (uint32_t)((p * g.Cin + c4) * 4));
-              const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                acc[o].x = fmaf(xs[e], w[e].x, acc[o].x);
-                acc[o].y = fmaf(xs[e], w[e].y, acc[o].y);
-                acc[o].z = fmaf(xs[e], w[e].z, acc[o].z);
-                acc[o].w = fmaf(xs[e], w[e].w, acc[o].w);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 w = lds128(wbase + (uint32_t)(((c4 + e) * g.Cr + k4 * 4) * 4));
+                acc_a[k4 * 4 + 0] = fmaf(a4[e], w.x, acc_a[k4 * 4 + 0]);
+                acc_a[k4 * 4 + 1] = fmaf(a4[e], w.y, acc_a[k4 * 4 + 1]);
+                acc_a[k4 * 4 + 2] = fmaf(a4[e], w.z, acc_a[k4 * 4 + 2]);
+                acc_a[k4 * 4 + 3] = fmaf(a4[e], w.w, acc_a[k4 * 4 + 3]);
+                acc_b[k4 * 4 + 0] = fmaf(b4[e], w.x, acc_b[k4 * 4 + 0]);
+                acc_b[k4 * 4 + 1] = fmaf(b4[e], w.y, acc_b[k4 * 4 + 1]);
+                acc_b[k4 * 4 + 2] = fmaf(b4[e], w.z, acc_b[k4 * 4 + 2]);
+                acc_b[k4 * 4 + 3] = fmaf(b4[e], w.w, acc_b[k4 * 4 + 3]);
               }
             }
           }
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const int p = p0 + o;
-            if (p >= P) break;
+          for (int two = 0; two < 2; ++two) {
+            const int p = two ? pb : pa;
+            if (p >= P) continue;
+            const float* acc = two ? acc_b : acc_a;
             const int ly = p / g.tw_in, lx = p - ly * g.tw_in;
             const int iy = iy0 + ly, ix = ix0 + lx;
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the map: the depthwise conv's zero padding
-            if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
-              y = make_float4(affine_rn(acc[o].x, sc.x, of.x), affine_rn(acc[o].y, sc.y, of.y),
-                              affine_rn(acc[o].z, sc.z, of.z), affine_rn(acc[o].w, sc.w, of.w));
-              if (g.e_act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+            const bool inside = iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the map: the depthwise conv's zero padding
+              if (inside) {
+                const float4 sc = lds128(smem_u32(s_e + cch + k4 * 4)), of = lds128(smem_u32(s_e + g.Cr + cch + k4 * 4));
+                y = make_float4(affine_rn(acc[k4 * 4 + 0], sc.x, of.x), affine_rn(acc[k4 * 4 + 1], sc.y, of.y),
+                                affine_rn(acc[k4 * 4 + 2], sc.z, of.z), affine_rn(acc[k4 * 4 + 3], sc.w, of.w));
+                if (g.e_act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+              }
+              const int chunk = (half * 4 + k4) ^ (p & 7);
+              sts128(hal + (uint32_t)(p * 128 + (chunk << 4)),
+                     make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
             }
-            sts128(hal + (uint32_t)(p * 128 + q * 16),
-                   make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
           }
         }
         __syncwarp();
@@ -766,6 +779,12 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+// WB_IRB=0 switches the fused block kernel off (the layers then run as separate GEMM / depthwise kernels)
+bool irb_enabled() {
+  const char* e = getenv("WB_IRB");
+  return e == nullptr || e[0] != '0';
 }
 
 struct IrbPlan {
@@ -908,7 +927,7 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
 // expand (1x1, ReLU6) -> depthwise 3x3 -> linear 1x1 projection [-> Add]: can the three (four) layers run as k_irb_x3?
 bool fused_irb_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& ex, const wb_layer& dw, const wb_layer& pw,
                          const wb_layer* add, int n) {
-  if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr || getenv("WB_NO_IRB") != nullptr) return false;
+  if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr || !irb_enabled()) return false;
   if (ex.op != WB_OP_PW || dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
   if (dw.in_off != ex.out_off || pw.in_off != dw.out_off) return false;
   if (ex.in_c > 32 || ex.in_c % 4 != 0 || (ex.in_c * 4) % 16 != 0) return false;  // CUDA-core expand: small K only

@@ -69,7 +69,7 @@ __device__ __forceinline__ float4 ld_dsmem128(uint32_t addr, uint32_t rank) {
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
   float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra));
   return v;
 }
 
@@ -92,11 +92,14 @@ __device__ __forceinline__ void copy_out_row(const TcArgs& g, const uint8_t* sme
     if (nn >= g.N) break;
     float4 y;
     if (reduce) {
-      y = ld_dsmem128(src + (uint32_t)(j * 4), 0);
-      for (int z = 1; z < members; ++z) {
-        const float4 p = ld_dsmem128(src + (uint32_t)(j * 4), (uint32_t)z);
-        y = make_float4(__fadd_rn(y.x, p.x), __fadd_rn(y.y, p.y), __fadd_rn(y.z, p.z), __fadd_rn(y.w, p.w));
-      }
+      float4 p[8];  // members <= 8 (portable cluster size): all remote loads in flight, then the ordered sum
+#pragma unroll
+      for (int z = 0; z < 8; ++z)
+        if (z < members) p[z] = ld_dsmem128(src + (uint32_t)(j * 4), (uint32_t)z);
+      y = p[0];
+#pragma unroll
+      for (int z = 1; z < 8; ++z)
+        if (z < members) y = make_float4(__fadd_rn(y.x, p[z].x), __fadd_rn(y.y, p[z].y), __fadd_rn(y.z, p[z].z), __fadd_rn(y.w, p[z].w));
       const float4 sc = *reinterpret_cast<const float4*>(g.scale + nn), of = *reinterpret_cast<const float4*>(g.offset + nn);
       y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
       if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
@@ -308,9 +311,44 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       }
     }
     __syncwarp();
+    if (threadIdx.x == 64) WB_STAMP(10, 0);
     if (!raw) {
       const int rows = min(g.rows_per_tile, g.M - m0);
-      for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 0);
+      if (g.is_head) {
+        for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 0);
+      } else {
+        // dense [M][N] output: the warp's 32 rows x block_n/4 float4 columns as one flat item list, 4 items per lane
+        // in flight (independent LDS.128 -> STG.128 pairs), consecutive lanes on consecutive 16-byte columns
+        const int c4n = g.block_n >> 2;
+        const int items = 32 * c4n;
+        const uint32_t sbase = smem_u32(smem);
+        for (int i0 = lane; i0 < items; i0 += 128) {
+          float4 y[4];
+          int rr[4], cc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            rr[u] = q * 32 + i / c4n;
+            cc[u] = (i - (i / c4n) * c4n) * 4;
+            if (i < items) y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u, nn = n0 + cc[u];
+            if (i >= items || rr[u] >= rows || nn >= g.N) continue;
+            const size_t o = (size_t)(m0 + rr[u]) * g.N + nn;
+            if (TF32) {
+              if (g.residual != nullptr) {
+                const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + o);
+                y[u] = make_float4(__fadd_rn(y[u].x, r4.x), __fadd_rn(y[u].y, r4.y), __fadd_rn(y[u].z, r4.z), __fadd_rn(y[u].w, r4.w));
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + o) = y[u];
+            } else {
+              ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + o, y[u]);
+            }
+          }
+        }
+      }
     }
     if (threadIdx.x == 64) WB_STAMP(6, 0);
   } else if (X3) {
@@ -380,6 +418,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     // all `splits` CTAs of this tile (one cluster) have staged their partial tiles
     __syncwarp();
     cluster_sync_all();
+    if (threadIdx.x == 64) WB_STAMP(11, 0);
     if (warp >= 2 && warp < 6) {
       const int rows = min(g.rows_per_tile, g.M - m0);
       const int z = (int)cluster_ctarank();
