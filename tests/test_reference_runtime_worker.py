@@ -35,5 +35,5 @@ def test_pipelined_worker_on_the_reference_runtime():
     assert sum(e[2] for e in submits) == 8 and max(e[2] for e in submits) <= 3
     # pipelining: the second submit happens before the first collect
     first_collect = next(i for i, e in enumerate(ev) if e[0] == 'collect')
-    assert sum(1 for e in ev[:first_collect] if e[0] == 'submit') == 2
+    assert sum(1 for e in ev[:first_collect] if e[0] == 'submit') >= 2
     assert r['device_name'] == 'FAKE-PIPE:0' and r['inference_time'] == 0.75 and not r['alive']

@@ -15,8 +15,8 @@ from multiprocessing import get_context
 
 import numpy as np
 
-DEPTH = 3          # ticks in flight between feeder and worker
-RING = 4           # frames per camera (> DEPTH, so a frame is never re-used while it is being detected)
+DEPTH = 6          # ticks in flight between feeder and worker (queue + the worker's pipeline slots)
+RING = 8           # frames per camera (> DEPTH, so a frame is never re-used while it is being detected)
 
 
 class CountingLatch(object):

@@ -8,13 +8,14 @@ detector.py:111-112), back-end constructed inside the child so that CUDA state i
 Differences from watsor/detection/detector.py:102-112: the worker drains every payload that is
 already waiting (at most one per camera: `BalancedQueue` holds a 1-slot semaphore per camera,
 sync.py:156-166) and hands them to the B200 as ONE batch; the shared-memory frames are page-locked once
-(`wb_register_host`) and the ticks are pipelined over two library slots (`submit` / `collect`): while the GPU
-runs tick k the worker writes back tick k-1 and drains the queue for tick k+1.  A frame's latch still advances
+(`wb_register_host`) and the ticks are pipelined over up to four library slots (`submit` / `collect`,
+`WATSOR_B200_PIPELINE_DEPTH`): while the GPU runs ticks k-2 .. k the worker writes back tick k-3 and drains the
+queue for tick k+1 -- a B200 needs several 8-frame batches in flight to be busy.  A frame's latch still advances
 exactly once, after its Detection rows are in its header (also when the back-end raises).
 """
 from collections import deque
 from multiprocessing.sharedctypes import Array
-from os import path
+from os import environ, path
 from queue import Empty
 
 from numpy import uint8
@@ -92,7 +93,7 @@ class ObjectDetector(Work):
                 self._in_flight = deque()
                 self._depth = 0
                 if callable(getattr(object_detector, 'submit', None)) and callable(getattr(object_detector, 'collect', None)):
-                    self._depth = max(1, min(int(kwargs.get('pipeline_depth', 2)), 6))
+                    self._depth = max(1, min(int(kwargs.get('pipeline_depth', environ.get('WATSOR_B200_PIPELINE_DEPTH', 4))), 6))
                     frame_buffers = args[2] if len(args) > 2 else {}
                     self._pin_frame_buffers(object_detector, frame_buffers)
                 try:
