@@ -240,12 +240,22 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     const int cut = s_cut;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long k = ck[i];  // second pass over the L2-resident keys
-      if (min((int)(k >> 52), 1023) >= cut)
-        s_a[atomicAdd(&s_na, 1)] = k;
-      else
-        s_b[atomicAdd(&s_nb, 1)] = k;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {  // second pass over the L2-resident keys
+      const int i = i0 + threadIdx.x;
+      const unsigned long long k = i < n ? ck[i] : 0ull;
+      const bool hi = i < n && min((int)(k >> 52), 1023) >= cut, lo = i < n && !hi;
+      // warp-aggregated append: one shared-memory atomic per warp and segment instead of one per key
+      const unsigned mh = __ballot_sync(0xffffffffu, hi), ml = __ballot_sync(0xffffffffu, lo);
+      int bh = 0, bl = 0;
+      if (lane == 0) {
+        if (mh) bh = atomicAdd(&s_na, __popc(mh));
+        if (ml) bl = atomicAdd(&s_nb, __popc(ml));
+      }
+      bh = __shfl_sync(0xffffffffu, bh, 0);
+      bl = __shfl_sync(0xffffffffu, bl, 0);
+      const unsigned lt = (1u << lane) - 1u;
+      if (hi) s_a[bh + __popc(mh & lt)] = k;
+      if (lo) s_b[bl + __popc(ml & lt)] = k;
     }
     __syncthreads();
     n_a = s_na;

@@ -897,9 +897,11 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   g.kb_per = g.k_blocks;
   g.partial = partial;
   const long tiles = (long)grid.x * grid.y;
-  if (tiles < 74 && g.k_blocks >= 4 && getenv("WB_NO_SPLITK") == nullptr) {
+  // A k-block costs ~850 cycles (profiles/r02_pipeline_trace.md) while the cluster barriers + DSMEM reduction of a split
+  // cost ~5-9 k cycles: splitting only pays for long accumulation chains, and every split keeps >= 8 k-blocks.
+  if (tiles < 74 && g.k_blocks >= 16 && getenv("WB_NO_SPLITK") == nullptr) {
     int want = (int)((148 + tiles - 1) / tiles);  // ~one CTA per SM of a B200
-    int splits = std::min(std::min(want, g.k_blocks / 2), 8);  // 8 = portable thread-block cluster size
+    int splits = std::min(std::min(want, g.k_blocks / 8), 8);  // 8 = portable thread-block cluster size
     if (splits > 1) {
       g.kb_per = (g.k_blocks + splits - 1) / splits;
       g.splits = (g.k_blocks + g.kb_per - 1) / g.kb_per;
