@@ -12,4 +12,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 
     --log-file gpurun_out/${T}_launches.csv python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/${T}_ncu.log 2>&1
 tail -1 gpurun_out/${T}_ncu.log | cut -c1-200
 echo "== trace (WB_TRACE rebuild on the box)"
-make -C watsor_b200/csrc -B EXTRA=-DWB_TRACE -j16 > /dev/null 2>&1 && timeout 300 python tools/trace_v2.py > gpurun_out/${T}_trace.txt 2>&1; tail -5 gpurun_out/${T}_trace.txt
+make -C watsor_b200/csrc -B EXTRA=-DWB_TRACE -j16 > /dev/null 2>&1 && timeout 300 python tools/trace_v2.py > gpurun_out/${T}_trace.txt 2>&1; timeout 300 python tools/trace_irb.py > gpurun_out/${T}_trace_irb.txt 2>&1; tail -5 gpurun_out/${T}_trace_irb.txt

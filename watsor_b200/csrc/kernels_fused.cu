@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WB_STAMP(9, 0);
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
@@ -503,6 +504,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         const int ib = j % g.in_stages;
         mbar_wait(smem_u32(&in_empty[ib]), ((j / g.in_stages) & 1) ^ 1);
         const uint32_t fb = smem_u32(&in_full[ib]);
+        WB_STAMP(0, j);
         mbar_expect_tx(fb, (uint32_t)(P * g.Cin * 4));
         tma_load_4d(smem_u32(in0 + (size_t)ib * in_bytes), &map_in, fb, 0, ox0 * S - g.pad_l, oy0 * S - g.pad_t, img);
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
           }
           umma_commit(smem_u32(&empty[s]));
           if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+          WB_STAMP(6, it);
         }
         __syncwarp();
       }
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
       mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) WB_STAMP(7, j);
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
       // this thread's output pixel (row q*32 + lane of the tile = spatial row 2q + lane/16, column lane%16)
       const int oy = oy0 + 2 * q + (lane >> 4), ox = ox0 + (lane & 15);
@@ -621,6 +625,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) WB_STAMP(8, j);
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
     }
     if (lane == 0) bulk_wait_read<0>();
@@ -642,6 +647,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         const float4 of = lds128(smem_u32(s_dw + 10 * g.Cr + cch));
         mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
         mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
+        if (pt == 0) WB_STAMP(4, it);
         const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
         const uint32_t a_hi = smem_u32(ab0 + (size_t)s * ab_bytes);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
@@ -690,6 +696,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         }
         fence_proxy_async();
         __syncwarp();
+        if (pt == 0) WB_STAMP(5, it);
         if (lane == 0) {
           mbar_arrive(smem_u32(&a_ready[s]));
           mbar_arrive(smem_u32(&halo_empty[h]));
@@ -710,9 +717,11 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       const int ib = j % g.in_stages;
       mbar_wait(smem_u32(&in_full[ib]), (j / g.in_stages) & 1);
       const uint32_t tin = smem_u32(in0 + (size_t)ib * in_bytes);
+      if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(1, j);
       for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
         const int h = it % g.halo_stages;
         mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
+        if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(2, it);
         const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
         for (int item = ew; item < n_items; item += IRB_EXPAND_WARPS) {
           const int half = item & 1, pbase = (item >> 1) * 64;
@@ -766,6 +775,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
           }
         }
         __syncwarp();
+        if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(3, it);
         if (lane == 0) mbar_arrive(smem_u32(&halo_full[h]));
       }
       __syncwarp();

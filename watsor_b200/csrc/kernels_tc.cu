@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) WB_STAMP(8, 0);  // kernel entry
+  if (threadIdx.x == 32) {  // descriptor fetch off the critical path of the first TMA load
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+  }
   const int m0 = blockIdx.x * g.rows_per_tile, n0 = blockIdx.y * g.block_n;
   const int kb0 = blockIdx.z * g.kb_per;
   __shared__ __align__(16) float s_scale[256], s_offset[256];
@@ -295,19 +300,54 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const bool raw = g.splits > 1;
     const int pitch = g.block_n + 4;
     const uint32_t stg_row = smem_u32(smem) + (uint32_t)(row * pitch * 4);
-    for (int c0 = 0; c0 < g.block_n; c0 += 16) {
-      uint32_t v[16];
-      load_acc16<X3>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g.block_n, g.n_main,
-                     min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES)), v);
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 y = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        if (!raw) {
-          const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
-          y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
-          if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+    {
+      // 16 columns per step; the tcgen05.ld of step k+1 are issued before step k is processed, so the TMEM round trip
+      // (the epilogue warps are latency bound: one warp per scheduler) overlaps the BN / staging work
+      const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int nch = g.block_n >> 4;
+      uint32_t bufs[2][4][16];  // [double buffer][main0, main1, main2, corr][16 columns]
+      auto issue = [&](int ch, int b) {
+        const uint32_t t = tbase + (uint32_t)(ch * 16);
+        tmem_ld16(t, bufs[b][0]);
+        if (X3) {
+          if (used > 1) tmem_ld16(t + (uint32_t)g.block_n, bufs[b][1]);
+          if (used > 2) tmem_ld16(t + (uint32_t)(2 * g.block_n), bufs[b][2]);
+          tmem_ld16(t + (uint32_t)(g.n_main * g.block_n), bufs[b][3]);
         }
-        sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
+      };
+      issue(0, 0);
+#pragma unroll 1
+      for (int ch = 0; ch < nch; ch += 2) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int c = ch + b;
+          if (c >= nch) break;
+          tmem_ld_wait();
+          if (c + 1 < nch) issue(c + 1, b ^ 1);
+          const int c0 = c * 16;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float y4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(bufs[b][0][j + e]);
+              if (X3) {  // fixed order ((main0 + main1) + main2) + corr, round to nearest
+                if (used > 1) a = __fadd_rn(a, __uint_as_float(bufs[b][1][j + e]));
+                if (used > 2) a = __fadd_rn(a, __uint_as_float(bufs[b][2][j + e]));
+                a = __fadd_rn(a, __uint_as_float(bufs[b][3][j + e]));
+              }
+              y4[e] = a;
+            }
+            float4 y = make_float4(y4[0], y4[1], y4[2], y4[3]);
+            if (!raw) {
+              const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
+              y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
+              if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
+            }
+            sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
+          }
+        }
       }
     }
     __syncwarp();
@@ -322,15 +362,22 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         const int c4n = g.block_n >> 2;
         const int items = 32 * c4n;
         const uint32_t sbase = smem_u32(smem);
+        const int inc_r = 32 / c4n, inc_c = 32 - inc_r * c4n;  // item index advances by 32 per step
+        int r_it = lane / c4n, c_it = lane - r_it * c4n;
         for (int i0 = lane; i0 < items; i0 += 128) {
           float4 y[4];
           int rr[4], cc[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u;
-            rr[u] = q * 32 + i / c4n;
-            cc[u] = (i - (i / c4n) * c4n) * 4;
-            if (i < items) y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+            rr[u] = q * 32 + r_it;
+            cc[u] = c_it * 4;
+            if (i0 + 32 * u < items) y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+            r_it += inc_r;
+            c_it += inc_c;
+            if (c_it >= c4n) {
+              c_it -= c4n;
+              ++r_it;
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -936,7 +983,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       g.n_main = std::max(1, std::min(3, 512 / g.block_n - 1));
       // short accumulation chains (split-K tails, small K) carry no measurable truncation bias: one main
       // accumulator halves the TMEM footprint, so two such CTAs can share an SM
-      if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;
+      if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 16) g.n_main = 1;
     }
     if (mode == TC_TF32X3 && !g.conv && getenv("WB_TMEM_A") != nullptr) {
       // experimental: A ring in tensor memory; chains of <= 32 steps per main accumulator
