@@ -642,9 +642,9 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         const int cch = kb * 32 + q * 4;
         float4 wr[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wr[k] = lds128(smem_u32(s_dw + k * g.Cr + cch));
-        const float4 sc = lds128(smem_u32(s_dw + 9 * g.Cr + cch));
-        const float4 of = lds128(smem_u32(s_dw + 10 * g.Cr + cch));
+        for (int k = 0; k < 9; ++k) wr[k] = lds128_ro(smem_u32(s_dw + k * g.Cr + cch));
+        const float4 sc = lds128_ro(smem_u32(s_dw + 9 * g.Cr + cch));
+        const float4 of = lds128_ro(smem_u32(s_dw + 10 * g.Cr + cch));
         mbar_wait(smem_u32(&halo_full[h]), (it / g.halo_stages) & 1);
         mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);  // A tiles of this stage are free again
         if (pt == 0) WB_STAMP(4, it);
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
             for (int e = 0; e < 4; ++e) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 w = lds128(wbase + (uint32_t)(((c4 + e) * g.Cr + k4 * 4) * 4));
+                const float4 w = lds128_ro(wbase + (uint32_t)(((c4 + e) * g.Cr + k4 * 4) * 4));
                 acc_a[k4 * 4 + 0] = fmaf(a4[e], w.x, acc_a[k4 * 4 + 0]);
                 acc_a[k4 * 4 + 1] = fmaf(a4[e], w.y, acc_a[k4 * 4 + 1]);
                 acc_a[k4 * 4 + 2] = fmaf(a4[e], w.z, acc_a[k4 * 4 + 2]);
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
             for (int k4 = 0; k4 < 4; ++k4) {
               float4 y = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the map: the depthwise conv's zero padding
               if (inside) {
-                const float4 sc = lds128(smem_u32(s_e + cch + k4 * 4)), of = lds128(smem_u32(s_e + g.Cr + cch + k4 * 4));
+                const float4 sc = lds128_ro(smem_u32(s_e + cch + k4 * 4)), of = lds128_ro(smem_u32(s_e + g.Cr + cch + k4 * 4));
                 y = make_float4(affine_rn(acc[k4 * 4 + 0], sc.x, of.x), affine_rn(acc[k4 * 4 + 1], sc.y, of.y),
                                 affine_rn(acc[k4 * 4 + 2], sc.z, of.z), affine_rn(acc[k4 * 4 + 3], sc.w, of.w));
                 if (g.e_act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));

@@ -93,9 +93,13 @@ __device__ __forceinline__ void copy_out_row(const TcArgs& g, const uint8_t* sme
     float4 y;
     if (reduce) {
       float4 p[8];  // members <= 8 (portable cluster size): all remote loads in flight, then the ordered sum
+      if (members == 1) {
+        p[0] = lds128(src + (uint32_t)(j * 4));
+      } else {
 #pragma unroll
-      for (int z = 0; z < 8; ++z)
-        if (z < members) p[z] = ld_dsmem128(src + (uint32_t)(j * 4), (uint32_t)z);
+        for (int z = 0; z < 8; ++z)
+          if (z < members) p[z] = ld_dsmem128(src + (uint32_t)(j * 4), (uint32_t)z);
+      }
       y = p[0];
 #pragma unroll
       for (int z = 1; z < 8; ++z)
@@ -165,7 +169,6 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   }
   const int m0 = blockIdx.x * g.rows_per_tile, n0 = blockIdx.y * g.block_n;
   const int kb0 = blockIdx.z * g.kb_per;
-  __shared__ __align__(16) float s_scale[256], s_offset[256];
   const int nkb = min(g.k_blocks, kb0 + g.kb_per) - kb0;  // k-blocks of this split (>= 1)
   // TF32X3 keeps n_main + 1 accumulators (see the MMA issuer); columns must be a power of two >= 32
   const int n_acc = X3 ? g.n_main + 1 : 1;
@@ -279,13 +282,6 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = row < g.rows_per_tile && m < g.M;
-    // while the k-loop runs: this tile's folded BN / bias columns -> shared memory
-    for (int j = threadIdx.x - 64; j < g.block_n; j += 128) {
-      const int nn = n0 + j;
-      s_scale[j] = nn < g.n_pad ? __ldg(g.scale + nn) : 1.f;
-      s_offset[j] = nn < g.n_pad ? __ldg(g.offset + nn) : 0.f;
-    }
-    epilogue_bar_sync();
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
     if (threadIdx.x == 64) WB_STAMP(5, 0);
@@ -339,12 +335,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
               }
               y4[e] = a;
             }
-            float4 y = make_float4(y4[0], y4[1], y4[2], y4[3]);
-            if (!raw) {
-              const float4 sc = lds128(smem_u32(s_scale + c0 + j)), of = lds128(smem_u32(s_offset + c0 + j));
-              y = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
-              if (g.act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
-            }
+            const float4 y = make_float4(y4[0], y4[1], y4[2], y4[3]);
             sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
           }
         }
@@ -355,7 +346,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     if (!raw) {
       const int rows = min(g.rows_per_tile, g.M - m0);
       if (g.is_head) {
-        for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 0);
+        for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 1);
       } else {
         // dense [M][N] output: the warp's 32 rows x block_n/4 float4 columns as one flat item list, 4 items per lane
         // in flight (independent LDS.128 -> STG.128 pairs), consecutive lanes on consecutive 16-byte columns
@@ -365,13 +356,18 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         const int inc_r = 32 / c4n, inc_c = 32 - inc_r * c4n;  // item index advances by 32 per step
         int r_it = lane / c4n, c_it = lane - r_it * c4n;
         for (int i0 = lane; i0 < items; i0 += 128) {
-          float4 y[4];
+          float4 y[4], sc[4], of[4];
           int rr[4], cc[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             rr[u] = q * 32 + r_it;
             cc[u] = c_it * 4;
-            if (i0 + 32 * u < items) y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+            if (i0 + 32 * u < items) {
+              y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+              // folded BN / bias of these 4 columns (every row re-reads the same few lines: L1 hits)
+              sc[u] = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + cc[u]));
+              of[u] = __ldg(reinterpret_cast<const float4*>(g.offset + n0 + cc[u]));
+            }
             r_it += inc_r;
             c_it += inc_c;
             if (c_it >= c4n) {
@@ -384,6 +380,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
             const int i = i0 + 32 * u, nn = n0 + cc[u];
             if (i >= items || rr[u] >= rows || nn >= g.N) continue;
             const size_t o = (size_t)(m0 + rr[u]) * g.N + nn;
+            y[u] = make_float4(affine_rn(y[u].x, sc[u].x, of[u].x), affine_rn(y[u].y, sc[u].y, of[u].y),
+                               affine_rn(y[u].z, sc[u].z, of[u].z), affine_rn(y[u].w, sc[u].w, of[u].w));
+            if (g.act == WB_ACT_RELU6) y[u] = make_float4(relu6f(y[u].x), relu6f(y[u].y), relu6f(y[u].z), relu6f(y[u].w));
             if (TF32) {
               if (g.residual != nullptr) {
                 const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + o);
