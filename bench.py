@@ -50,9 +50,10 @@ def parse_args():
     p.add_argument('--warmup', type=int, default=20)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--cameras', type=int, default=8, help='cameras (= batch) per GPU')
-    p.add_argument('--model', default='v2', choices=['v2', 'coco', 'shapes'],
+    p.add_argument('--model', default='v2', choices=['v2', 'coco', 'shapes', 'inception'],
                    help='v2: SSD-MobileNet-v2, 90 classes (BASELINE configs[2], default); coco: SSD-MobileNet-v1 '
-                        'backbone, 90-class heads; shapes: vendored 3-class SSD-MobileNet-v1 (real weights)')
+                        'backbone, 90-class heads; shapes: vendored 3-class SSD-MobileNet-v1 (real weights); '
+                        'inception: SSD-Inception-v2, 90 classes, 1920x1080 frames (BASELINE configs[4]; use --cameras 2)')
     p.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'bf16'],
                    help='fp32: CUDA-core FFMA convs; tf32x3: fp32-faithful tcgen05 (3xTF32 split); bf16: tcgen05 bf16')
     p.add_argument('--frames', default='artist', choices=['artist', 'random'])
@@ -78,12 +79,23 @@ def load_model(kind):
     if kind == 'shapes':
         return (synthetic_ssd_mobilenet_v1(num_classes=3, seed=1, score_thr=0.3),
                 'ssd_mobilenet_v1 300x300, 3 classes, seeded synthetic weights (vendored blob missing)')
+    if kind == 'inception':
+        from watsor_b200.model import synthetic_ssd_inception_v2
+        return (synthetic_ssd_inception_v2(num_classes=90, seed=0, score_thr=1e-8),
+                'ssd_inception_v2 300x300, 90 classes, score threshold 1e-8, seeded synthetic weights')
     if kind == 'v2':
         return (v2_coco_model(),
                 'ssd_mobilenet_v2 300x300, 90 classes, score threshold 1e-8, seeded synthetic weights '
                 '(no v2 weights exist offline)')
     return (synthetic_ssd_mobilenet_v1(num_classes=90, seed=0, score_thr=1e-8),
             'ssd_mobilenet_v1 300x300, 90-class heads, seeded synthetic weights')
+
+
+def set_frame_size(args):
+    """configs[4] (SSD-Inception-v2) is quoted on 1920x1080 streams; everything else on 640x480."""
+    global W, H
+    if args.model == 'inception':
+        W, H = 1920, 1080
 
 
 def make_frames(kind, cam, count):
@@ -98,6 +110,8 @@ def camera_config(cam, model_kind):
     """configs[2]: a mask on every camera, schema-default thresholds for every COCO label.  The 3-class
     real-weights model keeps round 1's configuration (its labels 1..3 are person/bicycle/car ids)."""
     from tests import workload
+    if model_kind == 'inception':
+        return workload.camera_config(cam % 8, W, H)
     if model_kind == 'shapes':
         detect = [{'person': {'confidence': 50, 'area': 1, 'zones': []}},
                   {'bicycle': {'confidence': 50, 'area': 1, 'zones': []}},
@@ -110,6 +124,10 @@ def camera_config(cam, model_kind):
 
 
 def workload_name(args):
+    if args.model == 'inception':
+        return ('BASELINE configs[4] per GPU: %d cameras x 1920x1080 synthetic RGB, batched, SSD-Inception-v2 300x300, '
+                '90-class NMS at score threshold 1e-8, a synthetic RGBA mask on every camera, per-class defaults '
+                'confidence 50 / area 10 (16 cameras on 8 GPUs = 2 per GPU)' % args.cameras)
     if args.model == 'shapes':
         return ('%d cameras x 640x480 synthetic RGB per GPU, batched, SSD-MobileNet-v1 300x300 (3 classes, real '
                 'weights), per-camera confidence/area filters + porch.png mask zones on camera 0' % args.cameras)
@@ -448,6 +466,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    set_frame_size(args)
     if args.impl == 'reference':
         run_reference(args, rank)
         return
@@ -518,7 +537,7 @@ def main():
 
     # ---------------- second record: the only model with real weights (round 1's headline configuration)
     real = None
-    if args.model != 'shapes' and not args.no_real_weights:
+    if args.model not in ('shapes', 'inception') and not args.no_real_weights:
         arm2 = Arm(args, 'shapes', rank, local_rank, world, torch, dist)
         r = arm2.measure()
         real = {'model': arm2.model_desc, 'workload': 'same frames; porch.png mask on camera 0, 3 labels',
@@ -535,7 +554,7 @@ def main():
             'vs_baseline': None, 'dtype': 'bf16' if arm.precision == 1 else 'f32', 'data': 'synthetic',
             'config': {
                 'workload': workload_name(args), 'cameras_per_gpu': C, 'global_batch': world * C,
-                'frame': '640x480x3 u8', 'model': arm.model_desc, 'frames': args.frames, 'ingest': args.ingest,
+                'frame': '%dx%dx3 u8' % (W, H), 'model': arm.model_desc, 'frames': args.frames, 'ingest': args.ingest,
                 'num_classes': arm.model.num_classes, 'score_threshold': arm.model.score_thr,
                 'masks': 'one per camera (cam 0: porch.png, 2 zones; cams 1..%d: synthetic RGBA, 1 + cam %% 4 zones)'
                          % (C - 1) if args.model != 'shapes' else 'porch.png on camera 0',
@@ -576,7 +595,7 @@ def measure_worker(args, local_rank, headline):
     except ImportError:
         return None
     try:
-        return run_worker_bench(args, local_rank, camera_config, load_model, make_frames)
+        return run_worker_bench(args, local_rank, camera_config, load_model, make_frames, width=W, height=H)
     except Exception as e:          # the headline number must not die with the auxiliary one
         return {'error': '%s: %s' % (type(e).__name__, e)}
 

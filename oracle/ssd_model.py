@@ -12,7 +12,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from watsor_b200.model import OP_ADD, OP_CONV, OP_DW, OP_HEAD, OP_PW, OP_STEM, Model
+from watsor_b200.model import (OP_ADD, OP_AVGPOOL, OP_CONV, OP_COPY, OP_DW, OP_HEAD, OP_MAXPOOL, OP_PW, OP_STEM,
+                               Model)
 
 from .ssd_graph import SsdGraphOracle
 
@@ -58,6 +59,28 @@ class SsdModelOracle(SsdGraphOracle):
                 x = x0 if l.op == OP_STEM else arena[l.in_off]
                 if l.op == OP_ADD:
                     v = x + arena[l.in2_off]
+                elif l.op in (OP_MAXPOOL, OP_AVGPOOL):
+                    # TF MaxPool / AvgPool, padding SAME: the maximum ignores the padding, the average divides by the
+                    # number of taps that fall inside the image
+                    pb = max((l.out_h - 1) * l.stride + l.kh - l.in_h - l.pad_t, 0)
+                    pr = max((l.out_w - 1) * l.stride + l.kw - l.in_w - l.pad_l, 0)
+                    if l.op == OP_MAXPOOL:
+                        xp = F.pad(x, (l.pad_l, pr, l.pad_t, pb), value=float('-inf'))
+                        v = F.max_pool2d(xp, (l.kh, l.kw), stride=l.stride)
+                    else:
+                        xp = F.pad(x, (l.pad_l, pr, l.pad_t, pb))
+                        ones = F.pad(torch.ones_like(x[:, :1]), (l.pad_l, pr, l.pad_t, pb))
+                        num = F.avg_pool2d(xp, (l.kh, l.kw), stride=l.stride, divisor_override=1)
+                        cnt = F.avg_pool2d(ones, (l.kh, l.kw), stride=l.stride, divisor_override=1)
+                        v = num / cnt
+                elif l.op == OP_COPY:
+                    dst = arena.get(('cat', l.out_off))
+                    if dst is None or dst.shape[1] != l.out_c:
+                        dst = torch.zeros((1, l.out_c, l.out_h, l.out_w), dtype=self.tdtype)
+                    dst = dst.clone()
+                    dst[:, l.row_off:l.row_off + l.in_c] = x
+                    arena[('cat', l.out_off)] = dst
+                    v = dst
                 else:
                     w = self._tt(l.w_tensor)
                     scale = self._tt(l.scale_tensor)[:l.out_c]

@@ -109,6 +109,10 @@ void launch_dw(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const
                const float* offset, T* out);
 template <typename T>
 void launch_add(const LaunchCtx& lc, size_t elems, const T* a, const T* b, T* out);
+template <typename T>
+void launch_pool(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, T* out);
+template <typename T>
+void launch_copy_channels(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, T* out);
 struct SplitKReduceArgs {
   const float* partial;  // [splits][M][ld] raw accumulators
   const float* scale;

@@ -152,6 +152,79 @@ void launch_add(const LaunchCtx& lc, size_t elems, const T* a, const T* b, T* ou
 template void launch_add<float>(const LaunchCtx&, size_t, const float*, const float*, float*);
 template void launch_add<__nv_bfloat16>(const LaunchCtx&, size_t, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*);
 
+// TF MaxPool / AvgPool with padding SAME (Inception modules): thread = (pixel, 4 channels).  The maximum ignores the
+// padding; the average is the fp32 sum of the in-image taps in (ky, kx) order divided by their count.
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(256) k_pool(int n, wb_layer L, const T* __restrict__ in, T* __restrict__ out) {
+  const int c4n = L.out_c >> 2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n * L.out_h * L.out_w * c4n;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4n) * 4;
+  size_t p = idx / c4n;
+  const int ox = (int)(p % L.out_w);
+  p /= L.out_w;
+  const int oy = (int)(p % L.out_h);
+  const int f = (int)(p / L.out_h);
+  const T* base = in + (size_t)f * L.in_h * L.in_w * L.in_c + c;
+  const int iy0 = oy * (int)L.stride - (int)L.pad_t, ix0 = ox * (int)L.stride - (int)L.pad_l;
+  float4 acc = MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int ky = 0; ky < (int)L.kh; ++ky) {
+    const int iy = iy0 + ky;
+    if (iy < 0 || iy >= (int)L.in_h) continue;
+    for (int kx = 0; kx < (int)L.kw; ++kx) {
+      const int ix = ix0 + kx;
+      if (ix < 0 || ix >= (int)L.in_w) continue;
+      const float4 x = ActIO<T>::ld4(base + ((size_t)iy * L.in_w + ix) * L.in_c);
+      if (MAX) {
+        acc = make_float4(fmaxf(acc.x, x.x), fmaxf(acc.y, x.y), fmaxf(acc.z, x.z), fmaxf(acc.w, x.w));
+      } else {
+        acc = make_float4(__fadd_rn(acc.x, x.x), __fadd_rn(acc.y, x.y), __fadd_rn(acc.z, x.z), __fadd_rn(acc.w, x.w));
+      }
+      ++cnt;
+    }
+  }
+  if (!MAX) {
+    const float d = (float)cnt;
+    acc = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
+  }
+  ActIO<T>::st4(out + idx * 4, acc);
+}
+template <typename T>
+void launch_pool(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, T* out) {
+  size_t total = (size_t)n * L.out_h * L.out_w * (L.out_c >> 2);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (L.op == WB_OP_MAXPOOL)
+    k_pool<T, true><<<blocks, 256, 0, lc.stream>>>(n, L, in, out);
+  else
+    k_pool<T, false><<<blocks, 256, 0, lc.stream>>>(n, L, in, out);
+  ++*lc.launch_counter;
+}
+template void launch_pool<float>(const LaunchCtx&, int, const wb_layer&, const float*, float*);
+template void launch_pool<__nv_bfloat16>(const LaunchCtx&, int, const wb_layer&, const __nv_bfloat16*, __nv_bfloat16*);
+
+// ConcatV2 along channels, one input: [n*h*w][in_c] -> channels [row_off, row_off + in_c) of [n*h*w][out_c]
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy_channels(size_t pixels, int in_c, int out_c, int coff, const T* __restrict__ in,
+                                                       T* __restrict__ out) {
+  const int c4n = in_c >> 2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * c4n) return;
+  const size_t p = idx / c4n;
+  const int c = (int)(idx - p * c4n) * 4;
+  ActIO<T>::st4(out + p * out_c + coff + c, ActIO<T>::ld4(in + p * in_c + c));
+}
+template <typename T>
+void launch_copy_channels(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, T* out) {
+  const size_t pixels = (size_t)n * L.out_h * L.out_w;
+  const size_t total = pixels * (L.in_c >> 2);
+  k_copy_channels<T><<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(pixels, (int)L.in_c, (int)L.out_c, (int)L.row_off, in, out);
+  ++*lc.launch_counter;
+}
+template void launch_copy_channels<float>(const LaunchCtx&, int, const wb_layer&, const float*, float*);
+template void launch_copy_channels<__nv_bfloat16>(const LaunchCtx&, int, const wb_layer&, const __nv_bfloat16*, __nv_bfloat16*);
+
 // ---------------------------------------------------------------------------------------------------
 // SGEMM  C[M,N] = A[M,K] * W[K,N]  (+ per-column affine, ReLU6)
 //   M = n*out_h*out_w rows (NHWC pixels), K = kh*kw*in_c, N = out_c.

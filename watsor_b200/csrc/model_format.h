@@ -5,7 +5,17 @@
 
 #define WB_MODEL_MAGIC "WB200M01"
 
-enum wb_op : uint32_t { WB_OP_STEM = 1, WB_OP_DW = 2, WB_OP_PW = 3, WB_OP_CONV = 4, WB_OP_ADD = 5, WB_OP_HEAD = 6 };
+enum wb_op : uint32_t {
+  WB_OP_STEM = 1,
+  WB_OP_DW = 2,
+  WB_OP_PW = 3,
+  WB_OP_CONV = 4,
+  WB_OP_ADD = 5,
+  WB_OP_HEAD = 6,
+  WB_OP_MAXPOOL = 7,  // TF MaxPool, padding SAME
+  WB_OP_AVGPOOL = 8,  // TF AvgPool, padding SAME (divides by the number of in-image taps)
+  WB_OP_COPY = 9      // ConcatV2 along channels: in_c channels -> channels [row_off, row_off + in_c) of an out_c-wide tensor
+};
 enum wb_act : uint32_t { WB_ACT_NONE = 0, WB_ACT_RELU6 = 1 };
 
 struct wb_model_header {  // 256 bytes

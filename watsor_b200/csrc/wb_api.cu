@@ -198,6 +198,12 @@ int wb_create(int device, const void* model_blob, size_t blob_bytes, int max_bat
       REQUIRE(L.in_c % 16 == 0, std::string("layer ") + L.name + ": KxK convs need in_c to be a multiple of 16");
     if (L.op == WB_OP_DW) REQUIRE(L.out_c % 4 == 0 && L.kh == 3 && L.kw == 3, "depthwise must be 3x3, C%4==0");
     if (L.op == WB_OP_PW || L.op == WB_OP_CONV) REQUIRE(L.out_c % 4 == 0, "out_c must be a multiple of 4");
+    if (L.op == WB_OP_MAXPOOL || L.op == WB_OP_AVGPOOL)
+      REQUIRE(L.out_c % 4 == 0 && L.in_c == L.out_c && L.kh >= 1 && L.kw >= 1, "pooling needs C % 4 == 0");
+    if (L.op == WB_OP_COPY)
+      REQUIRE(L.in_c % 4 == 0 && L.out_c % 4 == 0 && L.row_off % 4 == 0 && L.row_off + L.in_c <= L.out_c,
+              "channel copy: slice must be 4-aligned and inside the destination");
+    REQUIRE(L.op >= WB_OP_STEM && L.op <= WB_OP_COPY, std::string("layer ") + L.name + ": unknown op");
   }
   CK(cudaMalloc(&c->d_weights, floats * sizeof(float)));
   CK(cudaMemcpy(c->d_weights, p, floats * sizeof(float), cudaMemcpyHostToDevice));
@@ -454,6 +460,13 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
       }
       case WB_OP_ADD:
         launch_add<T>(lc, (size_t)n * L.out_h * L.out_w * L.out_c, in, in2, outp);
+        break;
+      case WB_OP_MAXPOOL:
+      case WB_OP_AVGPOOL:
+        launch_pool<T>(lc, n, L, in, outp);
+        break;
+      case WB_OP_COPY:
+        launch_copy_channels<T>(lc, n, L, in, outp);
         break;
       case WB_OP_PW:
       case WB_OP_CONV:

@@ -19,8 +19,8 @@ import numpy as np
 from .graphdef import GraphDef
 
 MAGIC = b'WB200M01'
-OP_STEM, OP_DW, OP_PW, OP_CONV, OP_ADD, OP_HEAD = 1, 2, 3, 4, 5, 6
-OP_NAMES = {1: 'stem', 2: 'dw', 3: 'pw', 4: 'conv', 5: 'add', 6: 'head'}
+OP_STEM, OP_DW, OP_PW, OP_CONV, OP_ADD, OP_HEAD, OP_MAXPOOL, OP_AVGPOOL, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_NAMES = {1: 'stem', 2: 'dw', 3: 'pw', 4: 'conv', 5: 'add', 6: 'head', 7: 'maxpool', 8: 'avgpool', 9: 'copy'}
 ACT_NONE, ACT_RELU6 = 0, 1
 HEADER_BYTES, LAYER_BYTES, TENSOR_BYTES = 256, 128, 16
 N_ALIGN = 16          # weight matrices are padded to a multiple of 16 output channels
@@ -70,7 +70,7 @@ class Layer:
     def macs(self):
         if self.op == OP_DW:
             return self.out_h * self.out_w * self.out_c * self.kh * self.kw
-        if self.op == OP_ADD:
+        if self.op in (OP_ADD, OP_MAXPOOL, OP_AVGPOOL, OP_COPY):
             return 0
         return self.out_h * self.out_w * self.out_c * self.kh * self.kw * self.in_c
 
@@ -178,7 +178,8 @@ class Model:
 
         for i, l in enumerate(self.layers):
             if l.dst:
-                where[l.dst] = alloc(size[l.dst])
+                if l.dst not in where:          # a concat tensor is written by several COPY layers: allocate it once
+                    where[l.dst] = alloc(size[l.dst])
                 l.out_off = where[l.dst]
             if l.src and l.src in where:
                 l.in_off = where[l.src]
@@ -311,6 +312,30 @@ class _Emitter:
         self.m.layers.append(Layer(op=OP_ADD, in_h=h, in_w=w_, in_c=c, out_h=h, out_w=w_, out_c=c,
                                    name=name, src=a, src2=b, dst=dst))
         self.shape[dst] = (h, w_, c)
+
+    def pool(self, name, src, dst, k, stride, kind):
+        """TF `MaxPool` / `AvgPool`, padding SAME (the average divides by the number of in-image taps)."""
+        h, w_, c = self.shape[src]
+        oh, pt = same_pad(h, k, stride)
+        ow, pl = same_pad(w_, k, stride)
+        self.m.layers.append(Layer(op=OP_MAXPOOL if kind == 'max' else OP_AVGPOOL, in_h=h, in_w=w_, in_c=c, out_h=oh,
+                                   out_w=ow, out_c=c, kh=k, kw=k, stride=stride, pad_t=pt, pad_l=pl, name=name,
+                                   src=src, dst=dst))
+        self.shape[dst] = (oh, ow, c)
+
+    def concat(self, name, srcs, dst):
+        """`ConcatV2` along channels: one COPY layer per input writes its channel slice of `dst`
+        (in_c = slice width, out_c = total width, row_off = first channel of the slice)."""
+        h, w_, _ = self.shape[srcs[0]]
+        total = sum(self.shape[s_][2] for s_ in srcs)
+        off = 0
+        for k, s_ in enumerate(srcs):
+            assert self.shape[s_][:2] == (h, w_)
+            c = self.shape[s_][2]
+            self.m.layers.append(Layer(op=OP_COPY, in_h=h, in_w=w_, in_c=c, out_h=h, out_w=w_, out_c=total, row_off=off,
+                                       name='%s/%d' % (name, k), src=s_, dst=dst))
+            off += c
+        self.shape[dst] = (h, w_, total)
 
     def head(self, name, src, w_box, b_box, w_cls, b_cls, row_off, num_classes_p1):
         """One GEMM per feature map: [box columns | class columns] (both 1x1 + bias)."""
@@ -674,6 +699,106 @@ def synthetic_ssd_mobilenet_v2(num_classes=90, seed=0, score_thr=1e-8, input_siz
         em.conv('layer_19_2_Conv2d_%d_3x3_s2_%d' % (j, out_c), 'x%da' % j, 'x%db' % j, he((3, 3, mid, out_c), 9 * mid),
                 s, o, 2, ACT_RELU6)
         cur, c_in = 'x%db' % j, out_c
+        feats.append(cur)
+    row, fmaps, head_layers = 0, [], []
+    for k, f in enumerate(feats):
+        h, w_, c = em.shape[f]
+        a = 3 if k == 0 else 6
+        fmaps.append((h, w_))
+        n0 = len(m.layers)
+        row += em.head('BoxPredictor_%d' % k, f, he((1, 1, c, a * 4), c) * 0.5,
+                       (0.05 * rng.standard_normal(a * 4)).astype(np.float32),
+                       he((1, 1, c, a * (num_classes + 1)), c) * np.float32(cls_gain),
+                       (cls_bias + 0.5 * rng.standard_normal(a * (num_classes + 1))).astype(np.float32),
+                       row, num_classes + 1)
+        head_layers.append(m.layers.pop(n0))
+    for hl in head_layers:
+        at = max(i for i, l in enumerate(m.layers) if l.dst == hl.src)
+        m.layers.insert(at + 1, hl)
+    m.num_anchors = row
+    m.anchors_tensor = m.add_tensor(ssd_anchors(fmaps))
+    m.plan_arena()
+    return m
+
+
+def synthetic_ssd_inception_v2(num_classes=90, seed=0, score_thr=1e-8, input_size=300, cls_gain=0.3, cls_bias=-4.5):
+    """SSD-Inception-v2 architecture descriptor (TF-slim inception_v2, depth multiplier 1.0, separable 7x7 stem;
+    SSD feature maps `Mixed_4c` 19x19x576 and `Mixed_5c` 10x10x1024 plus four 1x1 -> 3x3/s2 extra pairs 512/256/256/128,
+    as in ssd_inception_v2_feature_extractor) with seeded synthetic weights.  BASELINE.json configs[4] names this
+    model (ref: README.md:446-451 lists it among the supported zoo models); no weights exist offline, so it is checked
+    GPU-vs-oracle only.  Every conv is Conv2D + BatchNorm + ReLU6 (the extractor's conv_hyperparams in the zoo config).
+    Inception module: [1x1] | [1x1 -> 3x3] | [1x1 -> 3x3 -> 3x3] | [3x3 pool -> 1x1], concatenated along channels;
+    the stride-2 modules Mixed_4a / Mixed_5a have two conv branches and a max-pool branch."""
+    rng = np.random.default_rng(seed)
+    m = Model(name='ssd_inception_v2_synthetic_c%d' % num_classes, input_h=input_size, input_w=input_size,
+              num_classes=num_classes, score_thr=score_thr, iou_thr=0.6, pre_mul=float(np.float32(2.0 / 255.0)), pre_sub=1.0)
+    em = _Emitter(m)
+    em.shape['image'] = (input_size, input_size, 3)
+
+    def he(shape, fan_in, gain=2.0):
+        return (rng.standard_normal(shape) * np.sqrt(gain / fan_in)).astype(np.float32)
+
+    def bn(c, spread=0.1):
+        return ((1.0 + spread * rng.standard_normal(c)).astype(np.float32),
+                (spread * rng.standard_normal(c)).astype(np.float32))
+
+    def conv(name, src, out_c, k=1, stride=1):
+        c_in = em.shape[src][2]
+        s_, o_ = bn(out_c)
+        em.conv(name, src, name, he((k, k, c_in, out_c), k * k * c_in), s_, o_, stride, ACT_RELU6)
+        return name
+
+    # Conv2d_1a_7x7: separable_conv2d(depth_multiplier=8) = 7x7 depthwise 3 -> 24 (no BN / activation in between),
+    # then 1x1 24 -> 64.  The depthwise part with a channel multiplier is a dense 7x7 conv with block-diagonal weights.
+    wd = np.zeros((7, 7, 3, 24), np.float32)
+    for c in range(3):
+        wd[:, :, c, c * 8:(c + 1) * 8] = he((7, 7, 8), 49)
+    em.conv('Conv2d_1a_7x7/depthwise', 'image', 'c1dw', wd, np.ones(24, np.float32), np.zeros(24, np.float32), 2, ACT_NONE)
+    s_, o_ = bn(64)
+    em.conv('Conv2d_1a_7x7/pointwise', 'c1dw', 'c1', he((1, 1, 24, 64), 24), s_, o_, 1, ACT_RELU6)
+    em.pool('MaxPool_2a_3x3', 'c1', 'p2a', 3, 2, 'max')
+    cur = conv('Conv2d_2b_1x1', 'p2a', 64)
+    cur = conv('Conv2d_2c_3x3', cur, 192, 3)
+    em.pool('MaxPool_3a_3x3', cur, 'p3a', 3, 2, 'max')
+    cur = 'p3a'
+
+    def mixed(name, src, b0, b1, b2, b3, pool='avg'):
+        outs = [conv(name + '/b0_1x1', src, b0)]
+        t = conv(name + '/b1_1x1', src, b1[0])
+        outs.append(conv(name + '/b1_3x3', t, b1[1], 3))
+        t = conv(name + '/b2_1x1', src, b2[0])
+        t = conv(name + '/b2_3x3a', t, b2[1], 3)
+        outs.append(conv(name + '/b2_3x3b', t, b2[2], 3))
+        em.pool(name + '/b3_pool', src, name + '/b3p', 3, 1, pool)
+        outs.append(conv(name + '/b3_1x1', name + '/b3p', b3))
+        em.concat(name + '/concat', outs, name)
+        return name
+
+    def reduction(name, src, b0, b1):
+        t = conv(name + '/b0_1x1', src, b0[0])
+        o0 = conv(name + '/b0_3x3', t, b0[1], 3, 2)
+        t = conv(name + '/b1_1x1', src, b1[0])
+        t = conv(name + '/b1_3x3a', t, b1[1], 3)
+        o1 = conv(name + '/b1_3x3b', t, b1[2], 3, 2)
+        em.pool(name + '/b2_pool', src, name + '/b2p', 3, 2, 'max')
+        em.concat(name + '/concat', [o0, o1, name + '/b2p'], name)
+        return name
+
+    cur = mixed('Mixed_3b', cur, 64, (64, 64), (64, 96, 96), 32)
+    cur = mixed('Mixed_3c', cur, 64, (64, 96), (64, 96, 96), 64)
+    cur = reduction('Mixed_4a', cur, (128, 160), (64, 96, 96))
+    cur = mixed('Mixed_4b', cur, 224, (64, 96), (96, 128, 128), 128)
+    cur = mixed('Mixed_4c', cur, 192, (96, 128), (96, 128, 128), 128)
+    feat0 = cur
+    cur = mixed('Mixed_4d', cur, 160, (128, 160), (128, 160, 160), 96)
+    cur = mixed('Mixed_4e', cur, 96, (128, 192), (160, 192, 192), 96)
+    cur = reduction('Mixed_5a', cur, (128, 192), (192, 256, 256))
+    cur = mixed('Mixed_5b', cur, 352, (192, 320), (160, 224, 224), 128)
+    cur = mixed('Mixed_5c', cur, 352, (192, 320), (192, 224, 224), 128, pool='max')
+    feats = [feat0, cur]
+    for j, (mid, out_c) in enumerate([(256, 512), (128, 256), (128, 256), (64, 128)], 2):
+        t = conv('Mixed_5c_1_Conv2d_%d_1x1_%d' % (j, mid), cur, mid)
+        cur = conv('Mixed_5c_2_Conv2d_%d_3x3_s2_%d' % (j, out_c), t, out_c, 3, 2)
         feats.append(cur)
     row, fmaps, head_layers = 0, [], []
     for k, f in enumerate(feats):
