@@ -791,10 +791,12 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
   }
 }
 
-// WB_IRB=0 switches the fused block kernel off (the layers then run as separate GEMM / depthwise kernels)
+// WB_IRB=1 switches the fused block kernel on.  It is parity-green (tests/test_gpu_v2.py::test_irb_block_kernel) but
+// off by default: with the expand on CUDA cores the block costs 95-115 us where the separate tensor-core expand,
+// depthwise and projection kernels cost 48-75 us (profiles/r02_pipeline_trace.md has the per-role timeline).
 bool irb_enabled() {
   const char* e = getenv("WB_IRB");
-  return e == nullptr || e[0] != '0';
+  return e != nullptr && e[0] == '1';
 }
 
 struct IrbPlan {

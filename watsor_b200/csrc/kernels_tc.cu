@@ -276,128 +276,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ epilogue (TMEM -> global)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = row < g.rows_per_tile && m < g.M;
-    mbar_wait(smem_u32(acc_full), 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) WB_STAMP(5, 0);
-    // Every MMA has completed (acc_full), so the stage ring is dead: it becomes a [128][block_n + 4] fp32 staging
-    // tile.  Phase 1, thread = accumulator row: TMEM -> registers -> folded BN / bias (+ReLU6) -> staging (row pitch
-    // = 4 mod 16 words: the 8 lanes of a store phase hit 8 different bank groups).  Phase 2 (copy_out below), warp =
-    // rows, lanes along the columns: 128-byte coalesced stores.  The former epilogue stored 64 bytes per thread and
-    // row: 32 half-used sectors per instruction.
-    // Split-K: the `splits` CTAs of an output tile form one thread-block cluster; phase 1 stages the RAW partial
-    // accumulators, and after a cluster barrier CTA z reduces rows z, z + splits, ... over all members' staging tiles
-    // through distributed shared memory, always in the order z' = 0, 1, ... (deterministic), then runs the epilogue.
-    const bool raw = g.splits > 1;
-    const int pitch = g.block_n + 4;
-    const uint32_t stg_row = smem_u32(smem) + (uint32_t)(row * pitch * 4);
-    {
-      // 16 columns per step; the tcgen05.ld of step k+1 are issued before step k is processed, so the TMEM round trip
-      // (the epilogue warps are latency bound: one warp per scheduler) overlaps the BN / staging work
-      const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int nch = g.block_n >> 4;
-      uint32_t bufs[2][4][16];  // [double buffer][main0, main1, main2, corr][16 columns]
-      auto issue = [&](int ch, int b) {
-        const uint32_t t = tbase + (uint32_t)(ch * 16);
-        tmem_ld16(t, bufs[b][0]);
-        if (X3) {
-          if (used > 1) tmem_ld16(t + (uint32_t)g.block_n, bufs[b][1]);
-          if (used > 2) tmem_ld16(t + (uint32_t)(2 * g.block_n), bufs[b][2]);
-          tmem_ld16(t + (uint32_t)(g.n_main * g.block_n), bufs[b][3]);
-        }
-      };
-      issue(0, 0);
-#pragma unroll 1
-      for (int ch = 0; ch < nch; ch += 2) {
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int c = ch + b;
-          if (c >= nch) break;
-          tmem_ld_wait();
-          if (c + 1 < nch) issue(c + 1, b ^ 1);
-          const int c0 = c * 16;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float y4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(bufs[b][0][j + e]);
-              if (X3) {  // fixed order ((main0 + main1) + main2) + corr, round to nearest
-                if (used > 1) a = __fadd_rn(a, __uint_as_float(bufs[b][1][j + e]));
-                if (used > 2) a = __fadd_rn(a, __uint_as_float(bufs[b][2][j + e]));
-                a = __fadd_rn(a, __uint_as_float(bufs[b][3][j + e]));
-              }
-              y4[e] = a;
-            }
-            const float4 y = make_float4(y4[0], y4[1], y4[2], y4[3]);
-            sts128(stg_row + (uint32_t)((c0 + j) * 4), make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if (threadIdx.x == 64) WB_STAMP(10, 0);
-    if (!raw) {
-      const int rows = min(g.rows_per_tile, g.M - m0);
-      if (g.is_head) {
-        for (int r = q * 32; r < min(q * 32 + 32, rows); ++r) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 1);
-      } else {
-        // dense [M][N] output: the warp's 32 rows x block_n/4 float4 columns as one flat item list, 4 items per lane
-        // in flight (independent LDS.128 -> STG.128 pairs), consecutive lanes on consecutive 16-byte columns
-        const int c4n = g.block_n >> 2;
-        const int items = 32 * c4n;
-        const uint32_t sbase = smem_u32(smem);
-        const int inc_r = 32 / c4n, inc_c = 32 - inc_r * c4n;  // item index advances by 32 per step
-        int r_it = lane / c4n, c_it = lane - r_it * c4n;
-        for (int i0 = lane; i0 < items; i0 += 128) {
-          float4 y[4], sc[4], of[4];
-          int rr[4], cc[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            rr[u] = q * 32 + r_it;
-            cc[u] = c_it * 4;
-            if (i0 + 32 * u < items) {
-              y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
-              // folded BN / bias of these 4 columns (every row re-reads the same few lines: L1 hits)
-              sc[u] = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + cc[u]));
-              of[u] = __ldg(reinterpret_cast<const float4*>(g.offset + n0 + cc[u]));
-            }
-            r_it += inc_r;
-            c_it += inc_c;
-            if (c_it >= c4n) {
-              c_it -= c4n;
-              ++r_it;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u, nn = n0 + cc[u];
-            if (i >= items || rr[u] >= rows || nn >= g.N) continue;
-            const size_t o = (size_t)(m0 + rr[u]) * g.N + nn;
-            y[u] = make_float4(affine_rn(y[u].x, sc[u].x, of[u].x), affine_rn(y[u].y, sc[u].y, of[u].y),
-                               affine_rn(y[u].z, sc[u].z, of[u].z), affine_rn(y[u].w, sc[u].w, of[u].w));
-            if (g.act == WB_ACT_RELU6) y[u] = make_float4(relu6f(y[u].x), relu6f(y[u].y), relu6f(y[u].z), relu6f(y[u].w));
-            if (TF32) {
-              if (g.residual != nullptr) {
-                const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + o);
-                y[u] = make_float4(__fadd_rn(y[u].x, r4.x), __fadd_rn(y[u].y, r4.y), __fadd_rn(y[u].z, r4.z), __fadd_rn(y[u].w, r4.w));
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + o) = y[u];
-            } else {
-              ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + o, y[u]);
-            }
-          }
-        }
-      }
-    }
-    if (threadIdx.x == 64) WB_STAMP(6, 0);
-  } else if (X3) {
+  } else if (X3 && warp >= 6) {
     // ------------------------------------------------------------------ converters (A -> hi / lo)
     const int t = threadIdx.x - 192;  // 0..127
     if (TA) {
@@ -460,20 +339,136 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     }
   }
 
+  // ------------------------------------------------------------------ epilogue
+  // Every MMA has completed (acc_full), so the stage ring is dead: it becomes a [128][block_n + 4] fp32 staging tile
+  // (row pitch = 4 mod 16 words: the 8 lanes of a store phase hit 8 different bank groups).
+  // Phase 1 (warps 2.., thread = accumulator row): TMEM -> registers -> RAW accumulator sums -> staging.  A warp may
+  // read TMEM lane quarter warp % 4, so the four converter warps (idle by now) take every second 16-column chunk of
+  // "their" quarter: 8 warps instead of 4 on a phase that is bound by instruction latency, not bandwidth.
+  // Phase 2 (all warps, lanes along the columns): staging -> folded BN / bias, ReLU6, optional bottleneck shortcut ->
+  // 128-byte coalesced stores (dense [M][N], or the head scatter).
+  // Split-K: the `splits` CTAs of an output tile form one thread-block cluster; after a cluster barrier CTA z
+  // reduces rows z, z + splits, ... over all members' staging tiles through distributed shared memory, always in the
+  // order z' = 0, 1, ... (deterministic), then runs the same phase 2 arithmetic.
+  const int pitch = g.block_n + 4;
+  if (warp >= 2) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int part = warp >= 6 ? 1 : 0, parts = X3 ? 2 : 1;
+    mbar_wait(smem_u32(acc_full), 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) WB_STAMP(5, 0);
+    const uint32_t stg_row = smem_u32(smem) + (uint32_t)(row * pitch * 4);
+    // 16 columns per step; the tcgen05.ld of the next step are issued before this one is processed, so the TMEM
+    // round trip overlaps the staging work
+    const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nch = g.block_n >> 4;
+    uint32_t bufs[2][4][16];  // [double buffer][main0, main1, main2, corr][16 columns]
+    auto issue = [&](int ch, int b) {
+      const uint32_t t = tbase + (uint32_t)(ch * 16);
+      tmem_ld16(t, bufs[b][0]);
+      if (X3) {
+        if (used > 1) tmem_ld16(t + (uint32_t)g.block_n, bufs[b][1]);
+        if (used > 2) tmem_ld16(t + (uint32_t)(2 * g.block_n), bufs[b][2]);
+        tmem_ld16(t + (uint32_t)(g.n_main * g.block_n), bufs[b][3]);
+      }
+    };
+    if (part < nch) issue(part, 0);
+#pragma unroll 1
+    for (int ch = part; ch < nch; ch += 2 * parts) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int c = ch + b * parts;
+        if (c >= nch) break;
+        tmem_ld_wait();
+        if (c + parts < nch) issue(c + parts, b ^ 1);
+        const int c0 = c * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float y4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(bufs[b][0][j + e]);
+            if (X3) {  // fixed order ((main0 + main1) + main2) + corr, round to nearest
+              if (used > 1) a = __fadd_rn(a, __uint_as_float(bufs[b][1][j + e]));
+              if (used > 2) a = __fadd_rn(a, __uint_as_float(bufs[b][2][j + e]));
+              a = __fadd_rn(a, __uint_as_float(bufs[b][3][j + e]));
+            }
+            y4[e] = a;
+          }
+          sts128(stg_row + (uint32_t)((c0 + j) * 4),
+                 make_uint4(__float_as_uint(y4[0]), __float_as_uint(y4[1]), __float_as_uint(y4[2]), __float_as_uint(y4[3])));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();  // the staging tile is complete (and every TMEM read has retired)
+  if (threadIdx.x == 64) WB_STAMP(10, 0);
+  const int n_warps = blockDim.x >> 5;
+  const int rows = min(g.rows_per_tile, g.M - m0);
   if (g.splits > 1) {
     // all `splits` CTAs of this tile (one cluster) have staged their partial tiles
-    __syncwarp();
     cluster_sync_all();
     if (threadIdx.x == 64) WB_STAMP(11, 0);
-    if (warp >= 2 && warp < 6) {
-      const int rows = min(g.rows_per_tile, g.M - m0);
-      const int z = (int)cluster_ctarank();
-      for (int r = z + g.splits * (warp - 2); r < rows; r += 4 * g.splits)
-        copy_out_row<TF32>(g, smem, g.block_n + 4, r, m0, n0, lane, g.splits, 1);
-    }
+    const int z = (int)cluster_ctarank();
+    for (int r = z + g.splits * warp; r < rows; r += n_warps * g.splits)
+      copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, g.splits, 1);
     __syncwarp();
     cluster_sync_all();  // nobody exits while a peer still reads its staging tile
+  } else if (g.is_head) {
+    for (int r = warp; r < rows; r += n_warps) copy_out_row<TF32>(g, smem, pitch, r, m0, n0, lane, 1, 1);
+  } else {
+    // dense [M][N] output: the tile's rows x block_n/4 float4 columns as one flat item list over all threads, 4 items
+    // per thread in flight, consecutive lanes on consecutive 16-byte columns
+    const int c4n = g.block_n >> 2;
+    const int items = rows * c4n;
+    const int T = (int)blockDim.x;
+    const uint32_t sbase = smem_u32(smem);
+    const int inc_r = T / c4n, inc_c = T - inc_r * c4n;  // item index advances by T per step
+    int r_it = (int)threadIdx.x / c4n, c_it = (int)threadIdx.x - r_it * c4n;
+    for (int i0 = threadIdx.x; i0 < items; i0 += 4 * T) {
+      float4 y[4], sc[4], of[4];
+      int rr[4], cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        rr[u] = r_it;
+        cc[u] = c_it * 4;
+        if (i0 + T * u < items) {
+          y[u] = lds128(sbase + (uint32_t)((rr[u] * pitch + cc[u]) * 4));
+          // folded BN / bias of these 4 columns (every row re-reads the same few lines: L1 hits)
+          sc[u] = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + cc[u]));
+          of[u] = __ldg(reinterpret_cast<const float4*>(g.offset + n0 + cc[u]));
+        }
+        r_it += inc_r;
+        c_it += inc_c;
+        if (c_it >= c4n) {
+          c_it -= c4n;
+          ++r_it;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int nn = n0 + cc[u];
+        if (i0 + T * u >= items || nn >= g.N) continue;
+        const size_t o = (size_t)(m0 + rr[u]) * g.N + nn;
+        y[u] = make_float4(affine_rn(y[u].x, sc[u].x, of[u].x), affine_rn(y[u].y, sc[u].y, of[u].y),
+                           affine_rn(y[u].z, sc[u].z, of[u].z), affine_rn(y[u].w, sc[u].w, of[u].w));
+        if (g.act == WB_ACT_RELU6) y[u] = make_float4(relu6f(y[u].x), relu6f(y[u].y), relu6f(y[u].z), relu6f(y[u].w));
+        if (TF32) {
+          if (g.residual != nullptr) {
+            const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + o);
+            y[u] = make_float4(__fadd_rn(y[u].x, r4.x), __fadd_rn(y[u].y, r4.y), __fadd_rn(y[u].z, r4.z), __fadd_rn(y[u].w, r4.w));
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + o) = y[u];
+        } else {
+          ActIO<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16*>(g.out) + o, y[u]);
+        }
+      }
+    }
   }
+  if (threadIdx.x == 64) WB_STAMP(6, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
