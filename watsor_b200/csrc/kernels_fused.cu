@@ -371,25 +371,26 @@ bool make_plan(const wb_layer& dw, const wb_layer& pw, FusedPlan* p) {
 // MobileNet-v2 inverted residual block as ONE kernel (`expanded_conv_k/{expand,depthwise,project}` [+ `add`] of the
 // TF-slim graph a SSD-MobileNet-v2 frozen_inference_graph.pb holds; ref: watsor/detection/tensorflow_cpu.py:114 runs
 // them inside sess.run):
-//     1x1 expand (C_in <= 32 -> C, BN, ReLU6)  ->  depthwise 3x3 stride S (BN, ReLU6)  ->  1x1 linear projection
+//     1x1 expand (C_in <= 32 -> C, BN, ReLU6)  ->  depthwise 3x3 stride 1 (BN, ReLU6)  ->  1x1 linear projection
 //     (C -> N <= 128, BN)  [-> + shortcut]
-// The 6x expanded tensor (69 MB per batch of 8 at 150x150x96) and the depthwise output never leave the SM.
+// The 6x expanded tensor and the depthwise output never leave the SM; both 1x1 convolutions run on tcgen05.
 //
-// Persistent kernel, output tile = 8 x 16 pixels.  Per tile the TMA warp fetches the INPUT halo tile
-// ((7S+3) x (15S+3) pixels x C_in, out-of-image pixels zero-filled).  Then, per 32-channel block of the expanded
-// tensor:
-//   warps 14..21  expand producers: fp32 FFMA on CUDA cores (K = C_in is 16 .. 32: a tensor-core pass would need the
-//                 halo tile as a second swizzled hi/lo operand in shared memory, which does not fit beside the rest),
-//                 BN + ReLU6, zero outside the image (= the depthwise conv's SAME padding), written as the
-//                 depthwise halo chunk [pixels][32 ch]
-//   warps 6..13   depthwise producers: 3x3 window from the halo chunk, BN + ReLU6, TF32 hi/lo split, written
-//                 straight into the 128B-swizzled UMMA A tiles (same arithmetic as k_dwpw_tc_x3, stride 1 or 2)
-//   warp 5        tcgen05.mma issuer (3 TF32 MMAs per product), TMEM accumulator sets double-buffered
+// Persistent kernel, output tile = 8 x 16 pixels (one 128-row UMMA tile of the projection).  Per tile:
+//   warp 4        TMA: the INPUT halo tile (10 x 18 pixels x 32 channels, out-of-image pixels and channels >= C_in
+//                 zero-filled) lands 128B-swizzled = it IS the K-major A operand of the expand GEMM (180 rows, two
+//                 UMMA M tiles); per 32-channel block kb of the expanded tensor: the expand weight tiles (hi, lo)
+//                 and the projection weight tiles (hi, lo)
+//   warps 14..17  (a) once per tile: the TF32 `lo` copy of the input tile; (b) per kb, "mid-epilogue": expand
+//                 accumulators TMEM -> registers -> BN + ReLU6, zero outside the image (= the depthwise conv's SAME
+//                 padding) -> depthwise halo chunk [pixels][32 ch] in shared memory (XOR-swizzled 16-byte chunks)
+//   warps 6..13   depthwise producers: 3x3 window from the halo chunk, BN + ReLU6, TF32 hi/lo split, written straight
+//                 into the 128B-swizzled UMMA A tiles of the projection (same arithmetic as k_dwpw_tc_x3)
+//   warp 5        tcgen05.mma issuer for BOTH GEMMs (3 TF32 MMAs per product): expand(kb + 1) is issued before
+//                 projection(kb), so the tensor core works on the next chunk while the depthwise warps are busy
 //   warps 0..3    epilogue: tcgen05.ld -> BN (+ shortcut read from the block input) -> swizzled staging -> TMA store
-//   warp 4        TMA producer (input halo tiles, projection weight tiles hi / lo)
+// Stride-2 blocks are not fused: their 17 x 33 input halo needs 5 M tiles (hi + lo = 160 KB) beside a 72 KB halo chunk.
 struct IrbArgs {
-  const float* we;  // expand weights [C_in][we_ld]
-  const float* e_scale;
+  const float* e_scale;  // expand layer: folded BN [C]
   const float* e_offset;
   const float* dw_w;  // [9][C]
   const float* dw_scale;
@@ -397,36 +398,46 @@ struct IrbArgs {
   const float* scale;  // projection, [n_pad]
   const float* offset;
   const float* residual;  // block input [n][IH][IW][C_in] when the bottleneck Add is fused (C_in == N), else NULL
-  int we_ld, e_act, dw_act, act;
+  int e_act, dw_act, act;
   int Cin, C, Cr;  // Cr = C rounded up to 32
   int IH, IW, pad_t, pad_l, OH, OW, n_img;
   int N, n_pad, block_n, k_blocks, n_main;
-  int tiles_x, tiles_y, stages, halo_stages, in_stages, th_in, tw_in;
+  int tiles_x, tiles_y, stages, halo_stages, th_in, tw_in, m_tiles, e_ksteps;
 };
 
-constexpr int IRB_EXPAND_WARPS = 8;
-constexpr int IRB_FIRST_DW_THREAD = 192;                                             // warps 6..13
-constexpr int IRB_FIRST_EXPAND_THREAD = IRB_FIRST_DW_THREAD + 32 * F_PRODUCER_WARPS;  // warps 14..21
-constexpr int IRB_THREADS = IRB_FIRST_EXPAND_THREAD + 32 * IRB_EXPAND_WARPS;          // 704
+constexpr int IRB_XE_WARPS = 4;
+constexpr int IRB_FIRST_DW_THREAD = 192;                                          // warps 6..13
+constexpr int IRB_FIRST_XE_THREAD = IRB_FIRST_DW_THREAD + 32 * F_PRODUCER_WARPS;  // warps 14..17
+constexpr int IRB_THREADS = IRB_FIRST_XE_THREAD + 32 * IRB_XE_WARPS;              // 576
+constexpr int IRB_WE_STAGES = 2;
+constexpr int IRB_WE_BYTES = 2 * 32 * ROW_BYTES;  // expand weight tiles of one chunk: 32 channels x 32 k, hi + lo
 
 template <int S>
 __global__ void __launch_bounds__(IRB_THREADS, 1)
-    k_irb_x3(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+    k_irb_x3(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_we,
+             const __grid_constant__ CUtensorMap map_we_lo, const __grid_constant__ CUtensorMap map_b,
              const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out, IrbArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int P = g.th_in * g.tw_in;  // halo pixels
-  const int in_bytes = ((P * g.Cin * 4 + 1023) / 1024) * 1024;
+  const int P = g.th_in * g.tw_in;  // halo pixels = rows of the expand GEMM
+  const int ain_bytes = g.m_tiles * A_TILE_BYTES;
   const int halo_bytes = ((P * ROW_BYTES + 1023) / 1024) * 1024;
   const int b_tile_bytes = g.block_n * ROW_BYTES;
   const int ab_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-  uint8_t* in0 = smem;
-  uint8_t* halo0 = in0 + (size_t)g.in_stages * in_bytes;
+  uint8_t* ain_hi = smem;
+  uint8_t* ain_lo = ain_hi + ain_bytes;
+  uint8_t* we0 = ain_lo + ain_bytes;
+  uint8_t* halo0 = we0 + IRB_WE_STAGES * IRB_WE_BYTES;
   uint8_t* ab0 = halo0 + (size_t)g.halo_stages * halo_bytes;
   uint8_t* staging = ab0 + (size_t)g.stages * ab_bytes;
   uint64_t* in_full = reinterpret_cast<uint64_t*>(staging + F_STAGING_BYTES);
-  uint64_t* in_empty = in_full + 2;
-  uint64_t* halo_full = in_empty + 2;
+  uint64_t* in_ready = in_full + 1;
+  uint64_t* in_empty = in_ready + 1;
+  uint64_t* we_full = in_empty + 1;            // [2]
+  uint64_t* we_empty = we_full + IRB_WE_STAGES;  // [2]
+  uint64_t* eacc_full = we_empty + IRB_WE_STAGES;
+  uint64_t* eacc_empty = eacc_full + 1;
+  uint64_t* halo_full = eacc_empty + 1;
   uint64_t* halo_empty = halo_full + g.halo_stages;
   uint64_t* b_full = halo_empty + g.halo_stages;
   uint64_t* a_ready = b_full + g.stages;
@@ -435,25 +446,30 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_dw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [11][Cr]
-  float* s_pw = s_dw + 11 * g.Cr;      // [2][block_n]
-  float* s_e = s_pw + 2 * g.block_n;   // [2][Cr]: folded BN of the expand layer
-  float* s_we = s_e + 2 * g.Cr;        // [Cin][Cr]
+  float* s_pw = s_dw + 11 * g.Cr;     // [2][block_n]
+  float* s_e = s_pw + 2 * g.block_n;  // [2][Cr]: folded BN of the expand layer
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
   const int num_tiles = tiles_per_img * g.n_img;
   const int n_acc = g.n_main + 1;
   const int set_cols = n_acc * g.block_n;
+  const int e_cols = g.m_tiles * 64;  // per M tile: 32 main + 32 correction columns
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * set_cols) tmem_cols <<= 1;
+  while ((int)tmem_cols < e_cols + 2 * set_cols) tmem_cols <<= 1;
 
   if (warp == 4 && lane == 0) {
-    for (int i = 0; i < g.in_stages; ++i) {
-      mbar_init(smem_u32(&in_full[i]), 1);
-      mbar_init(smem_u32(&in_empty[i]), IRB_EXPAND_WARPS);
+    mbar_init(smem_u32(in_full), 1);
+    mbar_init(smem_u32(in_ready), IRB_XE_WARPS);
+    mbar_init(smem_u32(in_empty), 1);
+    for (int i = 0; i < IRB_WE_STAGES; ++i) {
+      mbar_init(smem_u32(&we_full[i]), 1);
+      mbar_init(smem_u32(&we_empty[i]), 1);
     }
+    mbar_init(smem_u32(eacc_full), 1);
+    mbar_init(smem_u32(eacc_empty), IRB_XE_WARPS);
     for (int h = 0; h < g.halo_stages; ++h) {
-      mbar_init(smem_u32(&halo_full[h]), IRB_EXPAND_WARPS);
+      mbar_init(smem_u32(&halo_full[h]), IRB_XE_WARPS);
       mbar_init(smem_u32(&halo_empty[h]), F_PRODUCER_WARPS);
     }
     for (int s = 0; s < g.stages; ++s) {
@@ -468,8 +484,8 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
-  // per-channel tables; channels C .. Cr-1 (the ragged last 32-block, e.g. C = 144) are zero: they expand to 0,
-  // convolve to 0 and meet zero-filled projection weights
+  // per-channel tables; channels C .. Cr-1 (the ragged last 32-block, e.g. C = 144) are zero: they expand to 0
+  // (zero-filled weight rows), convolve to 0 and meet zero-filled projection weights
   for (int i = threadIdx.x; i < 11 * g.Cr; i += blockDim.x) {
     const int k = i / g.Cr, c = i - k * g.Cr;
     float v = 0.f;
@@ -484,14 +500,16 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
     s_e[i] = i < g.C ? g.e_scale[i] : 0.f;
     s_e[g.Cr + i] = i < g.C ? g.e_offset[i] : 0.f;
   }
-  for (int i = threadIdx.x; i < g.Cin * g.Cr; i += blockDim.x) {
-    const int k = i / g.Cr, c = i - k * g.Cr;
-    s_we[i] = c < g.C ? g.we[(size_t)k * g.we_ld + c] : 0.f;
-  }
+  // rows P .. m_tiles*128-1 of the input operand are never written by TMA: zero them once so that the (unused) MMA
+  // rows stay finite
+  for (int i = threadIdx.x * 16; i < 2 * ain_bytes; i += blockDim.x * 16)
+    if ((i % ain_bytes) >= P * ROW_BYTES) sts128(smem_u32(ain_hi) + (uint32_t)i, make_uint4(0u, 0u, 0u, 0u));
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t e_col0 = (uint32_t)(2 * set_cols);  // expand accumulators behind the two projection sets
   if (threadIdx.x == 0) WB_STAMP(9, 0);
 
   if (warp == 4) {
@@ -501,14 +519,17 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
         const int img = t / tiles_per_img, r = t - img * tiles_per_img;
         const int oy0 = (r / g.tiles_x) * F_TH, ox0 = (r % g.tiles_x) * F_TW;
-        const int ib = j % g.in_stages;
-        mbar_wait(smem_u32(&in_empty[ib]), ((j / g.in_stages) & 1) ^ 1);
-        const uint32_t fb = smem_u32(&in_full[ib]);
+        mbar_wait(smem_u32(in_empty), (j & 1) ^ 1);  // the previous tile's expand MMAs have read the operand
         WB_STAMP(0, j);
-        mbar_expect_tx(fb, (uint32_t)(P * g.Cin * 4));
-        tma_load_4d(smem_u32(in0 + (size_t)ib * in_bytes), &map_in, fb, 0, ox0 * S - g.pad_l, oy0 * S - g.pad_t, img);
+        mbar_expect_tx(smem_u32(in_full), (uint32_t)(P * ROW_BYTES));
+        tma_load_4d(smem_u32(ain_hi), &map_in, smem_u32(in_full), 0, ox0 * S - g.pad_l, oy0 * S - g.pad_t, img);
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-          const int s = it % g.stages;
+          const int ws = it % IRB_WE_STAGES, s = it % g.stages;
+          mbar_wait(smem_u32(&we_empty[ws]), ((it / IRB_WE_STAGES) & 1) ^ 1);
+          const uint32_t wb = smem_u32(&we_full[ws]);
+          mbar_expect_tx(wb, IRB_WE_BYTES);
+          tma_load_2d(smem_u32(we0 + (size_t)ws * IRB_WE_BYTES), &map_we, wb, 0, kb * 32);
+          tma_load_2d(smem_u32(we0 + (size_t)ws * IRB_WE_BYTES + 32 * ROW_BYTES), &map_we_lo, wb, 0, kb * 32);
           mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
           const uint32_t bb = smem_u32(&b_full[s]);
           uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;
@@ -519,39 +540,71 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (expand and projection)
     const uint32_t idesc = make_idesc(true, BLOCK_M, g.block_n);
-    int it = 0, j = 0;
+    const uint32_t idesc_e = make_idesc(true, BLOCK_M, 32);
+    int it_e = 0, it_p = 0, j = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
       const int buf = j & 1;
-      mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
       const uint32_t acc0 = tmem_base + (uint32_t)(buf * set_cols);
-      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (it / g.stages) & 1;
-        mbar_wait(smem_u32(&a_ready[s]), ph);
-        mbar_wait(smem_u32(&b_full[s]), ph);
-        tc_fence_after();
-        if (elect_one()) {
-          uint8_t* st = ab0 + (size_t)s * ab_bytes;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
-          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
-#pragma unroll
-          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
-            const uint32_t koff = k * UMMA_K_BYTES;
-            const int step = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
-            const uint32_t d_main = acc0 + (uint32_t)((step % g.n_main) * g.block_n);
-            const uint32_t d_corr = acc0 + (uint32_t)(g.n_main * g.block_n);
-            umma<true>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, step >= g.n_main);
-            umma<true>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, step != 0);
-            umma<true>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+      mbar_wait(smem_u32(in_ready), j & 1);  // hi tile landed, lo tile written
+      for (int step = 0; step <= g.k_blocks; ++step) {
+        if (step < g.k_blocks) {
+          const int ws = it_e % IRB_WE_STAGES;
+          mbar_wait(smem_u32(&we_full[ws]), (it_e / IRB_WE_STAGES) & 1);
+          mbar_wait(smem_u32(eacc_empty), (it_e & 1) ^ 1);  // the mid-epilogue has drained the previous chunk
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t w_hi = smem_u32(we0 + (size_t)ws * IRB_WE_BYTES), w_lo = w_hi + 32 * ROW_BYTES;
+            for (int mt = 0; mt < g.m_tiles; ++mt) {
+              const uint32_t a_hi = smem_u32(ain_hi) + (uint32_t)(mt * A_TILE_BYTES), a_lo = a_hi + (uint32_t)ain_bytes;
+              const uint32_t d_main = tmem_base + e_col0 + (uint32_t)(mt * 64), d_corr = d_main + 32u;
+              for (int k = 0; k < g.e_ksteps; ++k) {
+                const uint32_t koff = k * UMMA_K_BYTES;
+                umma<true>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(w_hi + koff), idesc_e, k != 0);
+                umma<true>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(w_hi + koff), idesc_e, k != 0);
+                umma<true>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(w_lo + koff), idesc_e, 1u);
+              }
+            }
+            umma_commit(smem_u32(&we_empty[ws]));
+            umma_commit(smem_u32(eacc_full));
+            if (step == g.k_blocks - 1) umma_commit(smem_u32(in_empty));
+            WB_STAMP(2, it_e);
           }
-          umma_commit(smem_u32(&empty[s]));
-          if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
-          WB_STAMP(6, it);
+          __syncwarp();
+          ++it_e;
         }
-        __syncwarp();
+        if (step >= 1) {
+          const int kb = step - 1;
+          const int s = it_p % g.stages;
+          const uint32_t ph = (it_p / g.stages) & 1;
+          if (kb == 0) {
+            mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) & 1) ^ 1);
+          }
+          mbar_wait(smem_u32(&a_ready[s]), ph);
+          mbar_wait(smem_u32(&b_full[s]), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            uint8_t* st = ab0 + (size_t)s * ab_bytes;
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+            for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+              const uint32_t koff = k * UMMA_K_BYTES;
+              const int stp = kb * (ROW_BYTES / UMMA_K_BYTES) + k;
+              const uint32_t d_main = acc0 + (uint32_t)((stp % g.n_main) * g.block_n);
+              const uint32_t d_corr = acc0 + (uint32_t)(g.n_main * g.block_n);
+              umma<true>(d_main, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, stp >= g.n_main);
+              umma<true>(d_corr, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, stp != 0);
+              umma<true>(d_corr, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty[s]));
+            if (kb == g.k_blocks - 1) umma_commit(smem_u32(&acc_full[buf]));
+            WB_STAMP(6, it_p);
+          }
+          __syncwarp();
+          ++it_p;
+        }
       }
     }
   } else if (warp < 4) {
@@ -704,82 +757,80 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
       }
     }
   } else if (warp >= 14) {
-    // ------------------------------------------------------------------ expand producers (CUDA cores, fp32)
-    // warp-item = 64 consecutive halo pixels x 16 channels of the k-block: lane = pixel (two pixels per thread, 32
-    // apart), so the pixel loads are conflict-free 16-byte accesses and every weight vector (one broadcast LDS.128) feeds
-    // 8 FMAs.  Per c: acc += x[c] * w[c][:] in ascending c, fp32 FFMA (the same arithmetic as the CUDA-core GEMM).
-    const int ew = warp - 14;
-    const int n_items = ((P + 63) >> 6) * 2;
+    // ------------------------------------------------------------------ input lo-converters + mid-epilogue
+    const int xt = threadIdx.x - IRB_FIRST_XE_THREAD;  // 0..127
+    const int q = warp & 3;                            // TMEM lane quarter of this warp
     int it = 0, j = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
       const int img_r = t % tiles_per_img;
       const int iy0 = (img_r / g.tiles_x) * F_TH * S - g.pad_t, ix0 = (img_r % g.tiles_x) * F_TW * S - g.pad_l;
-      const int ib = j % g.in_stages;
-      mbar_wait(smem_u32(&in_full[ib]), (j / g.in_stages) & 1);
-      const uint32_t tin = smem_u32(in0 + (size_t)ib * in_bytes);
-      if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(1, j);
+      // (a) TF32 split of the input tile: hi stays as loaded (the tensor core truncates), lo = (x - hi) truncated
+      mbar_wait(smem_u32(in_full), j & 1);
+      if (xt == 0) WB_STAMP(1, j);
+      {
+        const uint32_t a = smem_u32(ain_hi), lo = smem_u32(ain_lo);
+        for (int i = xt; i < P * (ROW_BYTES / 16); i += 32 * IRB_XE_WARPS) {
+          const uint4 x = lds128u(a + i * 16);
+          uint4 l;
+          l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(x.x & 0xFFFFE000u))) & 0xFFFFE000u;
+          l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(x.y & 0xFFFFE000u))) & 0xFFFFE000u;
+          l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(x.z & 0xFFFFE000u))) & 0xFFFFE000u;
+          l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(x.w & 0xFFFFE000u))) & 0xFFFFE000u;
+          sts128(lo + i * 16, l);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(in_ready));
+      }
+      // (b) per 32-channel chunk: expand accumulators -> BN + ReLU6 -> depthwise halo chunk
       for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
         const int h = it % g.halo_stages;
+        mbar_wait(smem_u32(eacc_full), it & 1);
         mbar_wait(smem_u32(&halo_empty[h]), ((it / g.halo_stages) & 1) ^ 1);
-        if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(2, it);
+        tc_fence_after();
+        if (xt == 0) WB_STAMP(10, it);
         const uint32_t hal = smem_u32(halo0 + (size_t)h * halo_bytes);
-        for (int item = ew; item < n_items; item += IRB_EXPAND_WARPS) {
-          const int half = item & 1, pbase = (item >> 1) * 64;
-          const int cch = kb * 32 + half * 16;
-          const int pa = pbase + lane, pb = pbase + 32 + lane;
-          const uint32_t xa = tin + (uint32_t)(min(pa, P - 1) * g.Cin * 4), xb = tin + (uint32_t)(min(pb, P - 1) * g.Cin * 4);
-          const uint32_t wbase = smem_u32(s_we + cch);
-          float acc_a[16], acc_b[16];
+        const int cch = kb * 32;
+        for (int mt = 0; mt < g.m_tiles; ++mt) {
+          if (mt * 128 + q * 32 >= P) break;  // warp-uniform: this lane quarter holds no halo pixel
+          const int p = mt * 128 + q * 32 + lane;
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + e_col0 + (uint32_t)(mt * 64);
+          uint32_t vm[32], vc[32];
+          tmem_ld16(ta, vm);
+          tmem_ld16(ta + 16u, vm + 16);
+          tmem_ld16(ta + 32u, vc);
+          tmem_ld16(ta + 48u, vc + 16);
+          tmem_ld_wait();
+          const int ly = p / g.tw_in, lx = p - ly * g.tw_in;
+          const int iy = iy0 + ly, ix = ix0 + lx;
+          const bool inside = p < P && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+          if (p < P) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc_a[i] = acc_b[i] = 0.f;
-          for (int c4 = 0; c4 < g.Cin; c4 += 4) {
-            const float4 va = lds128(xa + (uint32_t)(c4 * 4)), vb = lds128(xb + (uint32_t)(c4 * 4));
-            const float a4[4] = {va.x, va.y, va.z, va.w}, b4[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 w = lds128_ro(wbase + (uint32_t)(((c4 + e) * g.Cr + k4 * 4) * 4));
-                acc_a[k4 * 4 + 0] = fmaf(a4[e], w.x, acc_a[k4 * 4 + 0]);
-                acc_a[k4 * 4 + 1] = fmaf(a4[e], w.y, acc_a[k4 * 4 + 1]);
-                acc_a[k4 * 4 + 2] = fmaf(a4[e], w.z, acc_a[k4 * 4 + 2]);
-                acc_a[k4 * 4 + 3] = fmaf(a4[e], w.w, acc_a[k4 * 4 + 3]);
-                acc_b[k4 * 4 + 0] = fmaf(b4[e], w.x, acc_b[k4 * 4 + 0]);
-                acc_b[k4 * 4 + 1] = fmaf(b4[e], w.y, acc_b[k4 * 4 + 1]);
-                acc_b[k4 * 4 + 2] = fmaf(b4[e], w.z, acc_b[k4 * 4 + 2]);
-                acc_b[k4 * 4 + 3] = fmaf(b4[e], w.w, acc_b[k4 * 4 + 3]);
-              }
-            }
-          }
-#pragma unroll
-          for (int two = 0; two < 2; ++two) {
-            const int p = two ? pb : pa;
-            if (p >= P) continue;
-            const float* acc = two ? acc_b : acc_a;
-            const int ly = p / g.tw_in, lx = p - ly * g.tw_in;
-            const int iy = iy0 + ly, ix = ix0 + lx;
-            const bool inside = iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
+            for (int k4 = 0; k4 < 8; ++k4) {
               float4 y = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the map: the depthwise conv's zero padding
               if (inside) {
                 const float4 sc = lds128_ro(smem_u32(s_e + cch + k4 * 4)), of = lds128_ro(smem_u32(s_e + g.Cr + cch + k4 * 4));
-                y = make_float4(affine_rn(acc[k4 * 4 + 0], sc.x, of.x), affine_rn(acc[k4 * 4 + 1], sc.y, of.y),
-                                affine_rn(acc[k4 * 4 + 2], sc.z, of.z), affine_rn(acc[k4 * 4 + 3], sc.w, of.w));
+                const float a0 = __fadd_rn(__uint_as_float(vm[k4 * 4 + 0]), __uint_as_float(vc[k4 * 4 + 0]));
+                const float a1 = __fadd_rn(__uint_as_float(vm[k4 * 4 + 1]), __uint_as_float(vc[k4 * 4 + 1]));
+                const float a2 = __fadd_rn(__uint_as_float(vm[k4 * 4 + 2]), __uint_as_float(vc[k4 * 4 + 2]));
+                const float a3 = __fadd_rn(__uint_as_float(vm[k4 * 4 + 3]), __uint_as_float(vc[k4 * 4 + 3]));
+                y = make_float4(affine_rn(a0, sc.x, of.x), affine_rn(a1, sc.y, of.y), affine_rn(a2, sc.z, of.z),
+                                affine_rn(a3, sc.w, of.w));
                 if (g.e_act == WB_ACT_RELU6) y = make_float4(relu6f(y.x), relu6f(y.y), relu6f(y.z), relu6f(y.w));
               }
-              const int chunk = (half * 4 + k4) ^ (p & 7);
-              sts128(hal + (uint32_t)(p * 128 + (chunk << 4)),
+              sts128(hal + (uint32_t)(p * 128 + ((k4 ^ (p & 7)) << 4)),
                      make_uint4(__float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w)));
             }
           }
         }
+        tc_fence_before();
         __syncwarp();
-        if (threadIdx.x == IRB_FIRST_EXPAND_THREAD) WB_STAMP(3, it);
-        if (lane == 0) mbar_arrive(smem_u32(&halo_full[h]));
+        if (xt == 0) WB_STAMP(11, it);
+        if (lane == 0) {
+          mbar_arrive(smem_u32(eacc_empty));
+          mbar_arrive(smem_u32(&halo_full[h]));
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&in_empty[ib]));  // the input tile may be overwritten
     }
   }
 
@@ -800,41 +851,43 @@ bool irb_enabled() {
 }
 
 struct IrbPlan {
-  int block_n, n_main, stages, halo_stages, in_stages, th_in, tw_in, tiles_x, tiles_y, Cr, k_blocks;
+  int block_n, n_main, stages, halo_stages, th_in, tw_in, tiles_x, tiles_y, Cr, k_blocks, m_tiles, e_ksteps;
   size_t smem;
 };
 
 bool make_irb_plan(const wb_layer& ex, const wb_layer& dw, const wb_layer& pw, IrbPlan* p) {
+  if (dw.stride != 1) return false;  // the stride-2 input halo (561 rows, hi + lo) does not fit beside the halo chunk
   p->block_n = ((int)pw.n_pad + 31) / 32 * 32;
   p->Cr = ((int)dw.out_c + 31) / 32 * 32;
   p->k_blocks = p->Cr / 32;
-  p->n_main = p->k_blocks * 4 <= 32 ? 1 : 2;  // accumulation chains longer than 32 MMAs rotate over two accumulators
+  p->n_main = p->k_blocks * 4 <= 16 ? 1 : 2;  // longer accumulation chains rotate over two accumulators
   p->th_in = (F_TH - 1) * dw.stride + 3;
   p->tw_in = (F_TW - 1) * dw.stride + 3;
   p->tiles_x = (dw.out_w + F_TW - 1) / F_TW;
   p->tiles_y = (dw.out_h + F_TH - 1) / F_TH;
-  if (2 * (p->n_main + 1) * p->block_n > 512) return false;
   const size_t P = (size_t)p->th_in * p->tw_in;
-  const size_t in_b = (P * ex.in_c * 4 + 1023) / 1024 * 1024;
+  p->m_tiles = (int)((P + BLOCK_M - 1) / BLOCK_M);
+  p->e_ksteps = ((int)ex.in_c + 7) / 8;
+  if (p->m_tiles * 64 + 2 * (p->n_main + 1) * p->block_n > 512) return false;  // tensor memory columns
+  const size_t ain = 2 * (size_t)p->m_tiles * A_TILE_BYTES;
   const size_t halo = (P * ROW_BYTES + 1023) / 1024 * 1024;
   const size_t ab = 2 * A_TILE_BYTES + 2 * (size_t)p->block_n * ROW_BYTES;
-  const size_t tables = 4 * ((size_t)11 * p->Cr + 2 * p->block_n + 2 * p->Cr + (size_t)ex.in_c * p->Cr) + 64;
-  const size_t fixed = F_STAGING_BYTES + 1024 + 8 * 32 + tables;
+  const size_t tables = 4 * ((size_t)11 * p->Cr + 2 * p->block_n + 2 * p->Cr) + 64;
+  const size_t fixed = ain + IRB_WE_STAGES * IRB_WE_BYTES + F_STAGING_BYTES + 1024 + 8 * 32 + tables;
   const size_t budget = 227 * 1024;
-  // preference: two A/B stages and two halo chunks (overlap of expand / depthwise / MMA), then a second input tile
-  const int opts[5][3] = {{2, 2, 2}, {2, 2, 1}, {1, 2, 1}, {2, 1, 1}, {1, 1, 1}};  // {stages, halo_stages, in_stages}
+  const int opts[3][2] = {{2, 2}, {1, 2}, {1, 1}};  // {A/B stages, halo chunks}
   for (auto& o : opts) {
-    const size_t need = o[2] * in_b + o[1] * halo + o[0] * ab + fixed;
+    const size_t need = o[1] * halo + o[0] * ab + fixed;
     if (need <= budget) {
       p->stages = o[0];
       p->halo_stages = o[1];
-      p->in_stages = o[2];
       p->smem = need;
       return true;
     }
   }
   return false;
 }
+
 }  // namespace
 
 bool fused_dwpw_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& dw, const wb_layer& pw, int n) {
@@ -939,11 +992,12 @@ int fused_launch_dwpw(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_ind
 // expand (1x1, ReLU6) -> depthwise 3x3 -> linear 1x1 projection [-> Add]: can the three (four) layers run as k_irb_x3?
 bool fused_irb_supported(const TcWeights& tw, int pw_layer_index, const wb_layer& ex, const wb_layer& dw, const wb_layer& pw,
                          const wb_layer* add, int n) {
+  if (pw_layer_index < 2 || !tw.layers[pw_layer_index - 2].ready) return false;  // expand weights (hi / lo, K-major)
   if (tw.mode != TC_TF32X3 || getenv("WB_NO_FUSE") != nullptr || !irb_enabled()) return false;
   if (ex.op != WB_OP_PW || dw.op != WB_OP_DW || pw.op != WB_OP_PW) return false;
   if (dw.in_off != ex.out_off || pw.in_off != dw.out_off) return false;
   if (ex.in_c > 32 || ex.in_c % 4 != 0 || (ex.in_c * 4) % 16 != 0) return false;  // CUDA-core expand: small K only
-  if (dw.kh != 3 || dw.kw != 3 || (dw.stride != 1 && dw.stride != 2)) return false;
+  if (dw.kh != 3 || dw.kw != 3 || dw.stride != 1) return false;
   if (dw.out_c % 16 != 0 || ex.out_c != dw.out_c || pw.in_c != dw.out_c || pw.n_pad > 128 || pw.out_c % 4 != 0) return false;
   if (!tw.layers[pw_layer_index].ready) return false;
   IrbPlan p;
@@ -966,15 +1020,15 @@ int fused_launch_irb(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_inde
                      const wb_layer& dw, const wb_layer& pw, bool with_add, const void* in, const float* ex_w,
                      const float* ex_scale, const float* ex_offset, const float* dw_w, const float* dw_scale,
                      const float* dw_offset, const float* scale, const float* offset, void* out, std::string* err) {
+  (void)ex_w;
   const TcLayerWeights& w = tw.layers[pw_layer_index];
+  const TcLayerWeights& we = tw.layers[pw_layer_index - 2];
   IrbPlan p;
   if (!make_irb_plan(ex, dw, pw, &p)) {
     *err = "fused inverted residual block: no shared-memory plan";
     return 1;
   }
   IrbArgs g;
-  g.we = ex_w;
-  g.we_ld = ex.n_pad;
   g.e_scale = ex_scale;
   g.e_offset = ex_offset;
   g.dw_w = dw_w;
@@ -1005,16 +1059,19 @@ int fused_launch_irb(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_inde
   g.tiles_y = p.tiles_y;
   g.stages = p.stages;
   g.halo_stages = p.halo_stages;
-  g.in_stages = p.in_stages;
   g.th_in = p.th_in;
   g.tw_in = p.tw_in;
-  alignas(64) CUtensorMap map_in, map_out, map_b, map_b_lo;
+  g.m_tiles = p.m_tiles;
+  g.e_ksteps = p.e_ksteps;
+  alignas(64) CUtensorMap map_in, map_out, map_b, map_b_lo, map_we, map_we_lo;
   {
+    // the input halo tile is the K-major A operand of the expand GEMM: 128-byte rows (32 channels, zero-filled beyond
+    // C_in), 128B swizzle, rows in (y, x) order of the halo
     unsigned long long dims[4] = {(unsigned long long)ex.in_c, ex.in_w, ex.in_h, (unsigned long long)n};
     unsigned long long st[3] = {(unsigned long long)ex.in_c * 4, (unsigned long long)ex.in_w * ex.in_c * 4,
                                 (unsigned long long)ex.in_h * ex.in_w * ex.in_c * 4};
-    unsigned box[4] = {(unsigned)ex.in_c, (unsigned)p.tw_in, (unsigned)p.th_in, 1};
-    if (!tc_encode_map(&map_in, in, 4, 4, dims, st, box, false, err)) return 1;
+    unsigned box[4] = {32, (unsigned)p.tw_in, (unsigned)p.th_in, 1};
+    if (!tc_encode_map(&map_in, in, 4, 4, dims, st, box, true, err)) return 1;
   }
   {
     unsigned long long dims[4] = {(unsigned long long)pw.out_c, pw.out_w, pw.out_h, (unsigned long long)n};
@@ -1030,10 +1087,17 @@ int fused_launch_irb(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_inde
     if (!tc_encode_map(&map_b, w.w, 4, 2, dims, st, box, true, err)) return 1;
     if (!tc_encode_map(&map_b_lo, w.w_lo, 4, 2, dims, st, box, true, err)) return 1;
   }
+  {
+    // expand weights [n_pad = C (padded)][K = C_in] K-major: one tile = 32 expanded channels x 32 k (zero-filled)
+    unsigned long long dims[2] = {(unsigned long long)we.k, (unsigned long long)we.n_pad};
+    unsigned long long st[1] = {(unsigned long long)we.k * 4};
+    unsigned box[2] = {32, 32};
+    if (!tc_encode_map(&map_we, we.w, 4, 2, dims, st, box, true, err)) return 1;
+    if (!tc_encode_map(&map_we_lo, we.w_lo, 4, 2, dims, st, box, true, err)) return 1;
+  }
   static PerDeviceFlag attr_done;
   if (!attr_done.get()) {
     cudaError_t e = cudaFuncSetAttribute(k_irb_x3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_irb_x3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
       return 1;
@@ -1051,14 +1115,10 @@ int fused_launch_irb(const LaunchCtx& lc, const TcWeights& tw, int pw_layer_inde
   }
   const long tiles = (long)p.tiles_x * p.tiles_y * n;
   const dim3 grid((unsigned)std::min<long>(tiles, ctas));
-  if (dw.stride == 1)
-    k_irb_x3<1><<<grid, IRB_THREADS, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
-  else
-    k_irb_x3<2><<<grid, IRB_THREADS, p.smem, lc.stream>>>(map_in, map_b, map_b_lo, map_out, g);
+  k_irb_x3<1><<<grid, IRB_THREADS, p.smem, lc.stream>>>(map_in, map_we, map_we_lo, map_b, map_b_lo, map_out, g);
   ++*lc.launch_counter;
   return 0;
 }
-
 
 #ifdef WB_TRACE
 extern "C" int wb_trace_read_fused(long long* dst) {

@@ -428,6 +428,54 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const uint32_t sbase = smem_u32(smem);
     const int inc_r = T / c4n, inc_c = T - inc_r * c4n;  // item index advances by T per step
     int r_it = (int)threadIdx.x / c4n, c_it = (int)threadIdx.x - r_it * c4n;
+    if (inc_c == 0 && TF32) {
+      // the thread count is a multiple of the row length (block_n = 16/32/64/80/128/160): a thread keeps its 4 columns
+      // and walks down the rows -- folded BN / bias in registers, pointers advanced by a constant, ~20 instructions per
+      // float4 instead of ~50 (this phase is issue bound: 2.5 warps per scheduler)
+      const int nn = n0 + c_it * 4;
+      if (nn < g.N && r_it < rows) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + nn)), of = __ldg(reinterpret_cast<const float4*>(g.offset + nn));
+        const bool relu = g.act == WB_ACT_RELU6;
+        uint32_t sp = sbase + (uint32_t)((r_it * pitch + c_it * 4) * 4);
+        const uint32_t sstep = (uint32_t)(inc_r * pitch * 4);
+        float* op = reinterpret_cast<float*>(g.out) + (size_t)(m0 + r_it) * g.N + nn;
+        const float* rp = g.residual != nullptr ? reinterpret_cast<const float*>(g.residual) + (size_t)(m0 + r_it) * g.N + nn : nullptr;
+        const size_t gstep = (size_t)inc_r * g.N;
+        int r = r_it;
+        for (; r + 3 * inc_r < rows; r += 4 * inc_r) {
+          float4 y[4], rs[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            y[u] = lds128(sp + u * sstep);
+            if (rp != nullptr) rs[u] = *reinterpret_cast<const float4*>(rp + u * gstep);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float4 v = make_float4(affine_rn(y[u].x, sc.x, of.x), affine_rn(y[u].y, sc.y, of.y), affine_rn(y[u].z, sc.z, of.z),
+                                   affine_rn(y[u].w, sc.w, of.w));
+            if (relu) v = make_float4(relu6f(v.x), relu6f(v.y), relu6f(v.z), relu6f(v.w));
+            if (rp != nullptr) v = make_float4(__fadd_rn(v.x, rs[u].x), __fadd_rn(v.y, rs[u].y), __fadd_rn(v.z, rs[u].z), __fadd_rn(v.w, rs[u].w));
+            *reinterpret_cast<float4*>(op + u * gstep) = v;
+          }
+          sp += 4 * sstep;
+          op += 4 * gstep;
+          if (rp != nullptr) rp += 4 * gstep;
+        }
+        for (; r < rows; r += inc_r) {
+          const float4 y = lds128(sp);
+          float4 v = make_float4(affine_rn(y.x, sc.x, of.x), affine_rn(y.y, sc.y, of.y), affine_rn(y.z, sc.z, of.z), affine_rn(y.w, sc.w, of.w));
+          if (relu) v = make_float4(relu6f(v.x), relu6f(v.y), relu6f(v.z), relu6f(v.w));
+          if (rp != nullptr) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rp);
+            v = make_float4(__fadd_rn(v.x, r4.x), __fadd_rn(v.y, r4.y), __fadd_rn(v.z, r4.z), __fadd_rn(v.w, r4.w));
+            rp += gstep;
+          }
+          *reinterpret_cast<float4*>(op) = v;
+          sp += sstep;
+          op += gstep;
+        }
+      }
+    } else
     for (int i0 = threadIdx.x; i0 < items; i0 += 4 * T) {
       float4 y[4], sc[4], of[4];
       int rr[4], cc[4];
