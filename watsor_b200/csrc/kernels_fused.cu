@@ -523,13 +523,20 @@ __global__ void __launch_bounds__(IRB_THREADS, 1)
         WB_STAMP(0, j);
         mbar_expect_tx(smem_u32(in_full), (uint32_t)(P * ROW_BYTES));
         tma_load_4d(smem_u32(ain_hi), &map_in, smem_u32(in_full), 0, ox0 * S - g.pad_l, oy0 * S - g.pad_t, img);
-        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-          const int ws = it % IRB_WE_STAGES, s = it % g.stages;
-          mbar_wait(smem_u32(&we_empty[ws]), ((it / IRB_WE_STAGES) & 1) ^ 1);
+        // expand weights run one chunk ahead of the projection weights: the wait for a free A/B stage (= projection
+        // MMAs of an earlier chunk complete) must not hold back the expand GEMM of the next chunk
+        auto load_we = [&](int kb, int itw) {
+          const int ws = itw % IRB_WE_STAGES;
+          mbar_wait(smem_u32(&we_empty[ws]), ((itw / IRB_WE_STAGES) & 1) ^ 1);
           const uint32_t wb = smem_u32(&we_full[ws]);
           mbar_expect_tx(wb, IRB_WE_BYTES);
           tma_load_2d(smem_u32(we0 + (size_t)ws * IRB_WE_BYTES), &map_we, wb, 0, kb * 32);
           tma_load_2d(smem_u32(we0 + (size_t)ws * IRB_WE_BYTES + 32 * ROW_BYTES), &map_we_lo, wb, 0, kb * 32);
+        };
+        load_we(0, it);
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const int s = it % g.stages;
+          if (kb + 1 < g.k_blocks) load_we(kb + 1, it + 1);
           mbar_wait(smem_u32(&empty[s]), ((it / g.stages) & 1) ^ 1);
           const uint32_t bb = smem_u32(&b_full[s]);
           uint8_t* sb = ab0 + (size_t)s * ab_bytes + 2 * A_TILE_BYTES;

@@ -556,6 +556,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   uint64_t* acc_full = conv + g.stages;  // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // folded BN / bias of every output column, loaded once per CTA (the epilogue warps are latency bound: 64 global loads
+  // per 32-column chunk were most of their instruction stream)
+  float* s_so = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [2][n_pad]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.n_pad / g.block_n;
@@ -578,6 +581,10 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  for (int i = threadIdx.x; i < g.n_pad; i += blockDim.x) {
+    s_so[i] = g.scale[i];
+    s_so[g.n_pad + i] = g.offset[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -657,10 +664,15 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           uint32_t v[32];
           load_acc32<X3>(acc0 + (uint32_t)(c0 + h * 32), g.block_n, g.n_main, used, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; i += 4) {
             const int nn = n0 + c0 + h * 32 + i;
-            float x = affine_rn(__uint_as_float(v[i]), __ldg(g.scale + nn), __ldg(g.offset + nn));
-            y[h * 32 + i] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+            const float4 sc = lds128_ro(smem_u32(s_so + nn)), of = lds128_ro(smem_u32(s_so + g.n_pad + nn));
+            const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, ofs[4] = {of.x, of.y, of.z, of.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = affine_rn(__uint_as_float(v[i + e]), scs[e], ofs[e]);
+              y[h * 32 + i + e] = g.act == WB_ACT_RELU6 ? relu6f(x) : x;
+            }
           }
           if (TF32 && g.residual != nullptr && m0 + q * 32 + lane < g.M) {
             // MobileNet-v2 bottleneck `Add` fused behind the linear projection: (conv*scale + offset) + shortcut
@@ -1016,7 +1028,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   if (persist && mode != TC_TF32X3 && 2 * g.block_n > 512) persist = false;
   int stages;
   if (persist) {
-    stages = (225 * 1024 - STAGING_BYTES) / stage_bytes;
+    stages = (224 * 1024 - STAGING_BYTES - 8 * g.n_pad) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) persist = false;
   }
@@ -1049,7 +1061,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     const int staging = BLOCK_M * (g.block_n + 4) * 4;  // epilogue staging tile re-uses the stage ring
     g.ring_bytes = ((std::max(g.ring_bytes, staging) + 1023) / 1024) * 1024;
   }
-  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
+  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES + 8 * (size_t)g.n_pad + 32 : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
   alignas(64) CUtensorMap map_a;
   if (g.conv) {
     const int imgs = BLOCK_M / (int)(L.out_h * L.out_w);
