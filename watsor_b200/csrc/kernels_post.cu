@@ -210,9 +210,13 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_na = s_nb = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long k = ck[i];
-      atomicAdd(&s_hist[min((int)(k >> 52), 1023)], 1);  // sign + exponent + 3 mantissa bits of the score
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+      // scores of one class crowd into a handful of bins (most are ~0.01): aggregate equal bins inside the warp
+      // (__match_any_sync) so that one lane per distinct bin issues the shared-memory atomic
+      const int i = i0 + threadIdx.x;
+      const int bin = i < n ? min((int)(ck[i] >> 52), 1023) : -1;  // sign + exponent + 3 mantissa bits of the score
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
     }
     __syncthreads();
     if (warp == 0) {  // highest bins first until NMS_HEAD keys are covered
@@ -468,9 +472,12 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   // keys beyond a class's selection count were zeroed by k_nms, so the whole [C][MP] block can be read blindly
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const unsigned long long k = __ldg(keys + i);
-    if (k != 0ull) atomicAdd(&s_hist[(int)(k >> 53)], 1);
+  for (int i0 = 0; i0 < total; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const unsigned long long k = i < total ? __ldg(keys + i) : 0ull;
+    const int bin = k != 0ull ? (int)(k >> 53) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);  // equal bins inside the warp: one atomic
+    if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
   }
   __syncthreads();
   if (threadIdx.x < 32) {  // highest bins first until `want` keys are covered

@@ -855,8 +855,14 @@ bool tc_encode_map(void* map, const void* base, int elem_bytes, int rank, const 
 
 namespace {
 
-int pick_block_n(int n_pad) {
+int pick_block_n(int n_pad, int k_steps, int mode) {
   if (n_pad <= 128) return n_pad;  // multiples of 16 up to 128: one N tile
+  // A tcgen05.mma of the TF32 kinds covers only K = 8 and costs ~100 cycles whatever its width (profiles/
+  // r02_pipeline_trace.md), so wide instructions are the cheap ones: short accumulation chains (one main + one correction
+  // accumulator: 2 x 256 columns of tensor memory) take the widest tile (multiple of 16, <= 256) that divides N.
+  if (mode == TC_TF32X3 && k_steps <= 16 && getenv("WB_NO_WIDE_N") == nullptr)
+    for (int bn = 256; bn > 128; bn -= 16)
+      if (n_pad % bn == 0) return bn;
   int best = 16;
   for (int bn = 128; bn >= 16; bn -= 16)
     if (n_pad % bn == 0) {
@@ -891,7 +897,7 @@ int tc_prepare_weights(const std::vector<wb_layer>& layers, const std::vector<wb
     const float* src = host_data + tensors[L.w_tensor].offset;  // [K][NP]
     w.k = K;
     w.n_pad = NP;
-    w.block_n = pick_block_n(NP);
+    w.block_n = pick_block_n(NP, (K + 7) / 8, mode);
     const int elem = mode == TC_BF16 ? 2 : 4;
     const size_t bytes = (size_t)NP * K * elem;
     std::vector<uint8_t> hi(bytes), lo(mode == TC_TF32X3 ? bytes : 0);
