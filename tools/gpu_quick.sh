@@ -1,12 +1,8 @@
 #!/bin/bash
-# Quick iteration run: tensor-core tests, a short bench, the per-layer table of its JSON line.  Logs -> gpurun_out/
+# parity suite + default bench line (+ optional extra bench args in $2..)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tc.py -q --timeout=300 2>&1 | tail -5 | tee gpurun_out/quick_pytest.log
-timeout 600 python bench.py --steps 1000 --warmup 20 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/quick_bench.json
-python - <<'PY'
-import json
-d = json.load(open('gpurun_out/quick_bench.json'))
-print('value %.0f e2e %.0f ms/step %.4f launches/step %d' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['gpu_launches'] // d['steps']))
-print(' '.join('%s:%.4f' % (n.split('/')[-1][-14:], t) for n, t in d['config']['per_layer_ms'] if t > 0.006))
-print('sum %.4f' % sum(t for _, t in d['config']['per_layer_ms']))
-PY
+T=${1:-r2q}
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu --maxfail=8 -q -s --timeout 400 --timeout-method=thread 2>&1 | tail -150 > gpurun_out/${T}_pytest.log; grep -E "passed|failed|FAILED" gpurun_out/${T}_pytest.log | tail -8
+echo "== bench (default = configs[2])"
+timeout 900 python bench.py --steps 200 --warmup 10 2> gpurun_out/${T}_bench.err | tail -1 > gpurun_out/${T}_bench.json; cut -c1-300 gpurun_out/${T}_bench.json; tail -3 gpurun_out/${T}_bench.err

@@ -426,8 +426,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int items = rows * c4n;
     const int T = (int)blockDim.x;
     const uint32_t sbase = smem_u32(smem);
-    const int inc_r = T / c4n, inc_c = T - inc_r * c4n;  // item index advances by T per step
+    int inc_r = T / c4n, inc_c = T - inc_r * c4n;  // item index advances by T per step
     int r_it = (int)threadIdx.x / c4n, c_it = (int)threadIdx.x - r_it * c4n;
+    if (TF32 && inc_r >= 1) {
+      // use the largest thread count that is a multiple of the row length (block_n = 144: 288 of the 320 threads), so
+      // that every thread keeps its 4 columns
+      inc_c = 0;
+      if ((int)threadIdx.x >= inc_r * c4n) r_it = rows;  // surplus threads idle
+    }
     if (inc_c == 0 && TF32) {
       // the thread count is a multiple of the row length (block_n = 16/32/64/80/128/160): a thread keeps its 4 columns
       // and walks down the rows -- folded BN / bias in registers, pointers advanced by a constant, ~20 instructions per
@@ -860,7 +866,9 @@ int pick_block_n(int n_pad, int k_steps, int mode) {
   // A tcgen05.mma of the TF32 kinds covers only K = 8 and costs ~100 cycles whatever its width (profiles/
   // r02_pipeline_trace.md), so wide instructions are the cheap ones: short accumulation chains (one main + one correction
   // accumulator: 2 x 256 columns of tensor memory) take the widest tile (multiple of 16, <= 256) that divides N.
-  if (mode == TC_TF32X3 && k_steps <= 16 && getenv("WB_NO_WIDE_N") == nullptr)
+  // Measured (profiles/r02_final_summary.md): SM time of the 19x19 expansions -20 %, their latency +20 %, throughput with
+  // six batches in flight unchanged -> opt-in.
+  if (mode == TC_TF32X3 && k_steps <= 16 && getenv("WB_WIDE_N") != nullptr)
     for (int bn = 256; bn > 128; bn -= 16)
       if (n_pad % bn == 0) return bn;
   int best = 16;
@@ -1024,7 +1032,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  bool persist = !g.is_head && !g.conv && g.splits == 1 && tiles >= num_sms && g.N == g.n_pad && g.block_n % cw == 0 &&
+  bool persist = !g.is_head && !g.conv && g.splits == 1 && tiles >= num_sms && (g.N == g.n_pad || (g.N % 4 == 0 && mode != TC_BF16)) && g.block_n % cw == 0 &&
                  g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
   if (persist && mode == TC_TF32X3) {
     g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
