@@ -861,6 +861,17 @@ bool tc_encode_map(void* map, const void* base, int elem_bytes, int rank, const 
 
 namespace {
 
+int num_sms_hint() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int pick_block_n(int n_pad, int k_steps, int mode) {
   if (n_pad <= 128) return n_pad;  // multiples of 16 up to 128: one N tile
   // A tcgen05.mma of the TF32 kinds covers only K = 8 and costs ~100 cycles whatever its width (profiles/
@@ -1015,7 +1026,8 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   // A k-block costs ~850 cycles (profiles/r02_pipeline_trace.md) while the cluster barriers + DSMEM reduction of a split
   // cost ~5-9 k cycles: splitting only pays for long accumulation chains, and every split keeps >= 8 k-blocks.
   if (tiles < 74 && g.k_blocks >= 16 && getenv("WB_NO_SPLITK") == nullptr) {
-    int want = (int)((148 + tiles - 1) / tiles);  // ~one CTA per SM of a B200
+    int want = std::max(1, (int)(num_sms_hint() / tiles));  // at most one wave: tiles * splits <= SMs (a second wave of a
+                                                            // few CTAs doubles the kernel's duration)
     int splits = std::min(std::min(want, g.k_blocks / 8), 8);  // 8 = portable thread-block cluster size
     if (splits > 1) {
       g.kb_per = (g.k_blocks + splits - 1) / splits;
