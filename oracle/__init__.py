@@ -26,11 +26,19 @@ PARITY PINNING STATUS
     (watsor/test/test_filter.py:14-96), re-run against this oracle in
     tests/test_oracle_filters.py.
   - struct ABI: pinned by ctypes sizes/offsets of watsor/stream/share.py:11-32.
-  - conv / decode / NMS numerics: **parity unpinned**.  The reference holds no
-    golden boxes/scores for the TF graph (watsor/test/test_detect.py:28-77 only
-    asserts ">= 100 labelled detections with confidence >= 0.5"), and TensorFlow
-    cannot be run here.  The oracle is therefore checked against that same
-    behavioural assertion (Artist frames -> the drawn shapes are found with the
-    right class) and otherwise stands on its line-by-line restatement of the
-    GraphDef.
+  - conv / batch-norm / activation / bias numerics (backbone + heads, 99 % of the
+    arithmetic): pinned by an INDEPENDENT EXECUTOR of the reference's own graph --
+    OpenCV 4.13's dnn module run on the backbone + heads sub-graph of
+    watsor/test/model/cpu.pb (tools/make_golden_cvdnn.py, vectors in
+    tests/golden/cvdnn_heads.npz labelled "OpenCV-dnn, not TensorFlow",
+    tests/test_oracle_cvdnn.py: agreement to 4e-5 on tensors of range 21).
+  - legacy ResizeBilinear, anchor generator, box decode, sigmoid,
+    NonMaxSuppressionV5, top-100 assembly: **parity unpinned**.  The reference
+    holds no golden boxes/scores for the TF graph (watsor/test/test_detect.py:28-77
+    only asserts ">= 100 labelled detections with confidence >= 0.5"), and
+    TensorFlow cannot be run here.  These parts are checked against that same
+    behavioural assertion and otherwise stand on their line-by-line restatement of
+    the GraphDef and of TF's kernel semantics (quoted in oracle/ssd_graph.py).
+  - oracle/ties.py: float64 classification of rounding ties in the ranking (used by
+    the 90-class end-to-end tests); test infrastructure like the rest.
 """

@@ -1,7 +1,8 @@
 """CPU restatement of the frozen TF Object-Detection SSD graph that
 watsor/detection/tensorflow_cpu.py:104-121 runs with `sess.run`.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  "parity unpinned": the
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The conv stack is pinned by OpenCV-dnn running the same
+graph (tests/test_oracle_cvdnn.py); for resize / decode / NMS it is "parity unpinned": the
 reference holds no golden vectors at the TF boundary and TensorFlow cannot run
 here; this file follows the GraphDef node by node (node names quoted below) and is
 sanity-pinned on the reference's behavioural test (test_detect.py:28-77).
