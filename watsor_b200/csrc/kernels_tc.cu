@@ -137,8 +137,10 @@ __device__ __forceinline__ void copy_out_row(const TcArgs& g, const uint8_t* sme
 // TA (TF32X3 only, experimental, WB_TMEM_A=1): the converter warps write the hi / lo rows into tensor memory
 // (tcgen05.st) and the MMAs take A from there, so the shared-memory port carries neither the converter writes
 // nor the A operand reads.
-template <int MODE, bool TA = false>
-__global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
+// TWO: compiled for two co-resident CTAs per SM (<= 102 registers; the launcher keeps shared memory <= 110 KB and
+// tensor memory <= 256 columns).  The k-loop of one CTA then overlaps the prologue / epilogue of the other.
+template <int MODE, bool TA = false, bool TWO = false>
+__global__ void __launch_bounds__(MODE == 2 ? 320 : 192, TWO ? 2 : 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
   constexpr bool TF32 = MODE != 0;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     const int used = min(g.n_main, nkb * (ROW_BYTES / UMMA_K_BYTES));
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nch = g.block_n >> 4;
-    uint32_t bufs[2][4][16];  // [double buffer][main0, main1, main2, corr][16 columns]
+    uint32_t bufs[TWO ? 1 : 2][4][16];  // [double buffer][main0, main1, main2, corr][16 columns]
     auto issue = [&](int ch, int b) {
       const uint32_t t = tbase + (uint32_t)(ch * 16);
       tmem_ld16(t, bufs[b][0]);
@@ -374,15 +376,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         tmem_ld16(t + (uint32_t)(g.n_main * g.block_n), bufs[b][3]);
       }
     };
-    if (part < nch) issue(part, 0);
+    constexpr int NB = TWO ? 1 : 2;
+    if (!TWO && part < nch) issue(part, 0);
 #pragma unroll 1
-    for (int ch = part; ch < nch; ch += 2 * parts) {
+    for (int ch = part; ch < nch; ch += NB * parts) {
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < NB; ++b) {
         const int c = ch + b * parts;
         if (c >= nch) break;
+        if (TWO) issue(c, 0);
         tmem_ld_wait();
-        if (c + parts < nch) issue(c + parts, b ^ 1);
+        if (!TWO && c + parts < nch) issue(c + parts, b ^ 1);
         const int c0 = c * 16;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -1080,6 +1084,17 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     if (stages > 6) stages = 6;
     if (stages > g.kb_per) stages = g.kb_per;
   }
+  // Two CTAs per SM for short, epilogue-dominated layers (WB_GEMM_2CTA=1): <= 2 k-blocks, the stage ring cut down so
+  // that ring + staging tile fit in ~110 KB, <= 256 TMEM columns.
+  bool two = false;
+  if (!persist && mode == TC_TF32X3 && g.ta_stages == 0 && g.splits == 1 && getenv("WB_GEMM_2CTA") != nullptr) {
+    const int staging = BLOCK_M * (g.block_n + 4) * 4;
+    int st2 = std::min(stages, std::max(1, (108 * 1024) / stage_bytes));
+    if (g.kb_per <= 4 && std::max(st2 * stage_bytes, staging) <= 108 * 1024 && (g.n_main + 1) * g.block_n <= 256) {
+      stages = st2;
+      two = true;
+    }
+  }
   if (stages < 1) stages = 1;
   g.stages = stages;
   g.ring_bytes = stages * stage_bytes;
@@ -1173,6 +1188,13 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       ta_attr_done.set();
     }
     if (e == cudaSuccess) e = launch(k_gemm_tc<2, true>, 320);
+  } else if (two) {
+    static PerDeviceFlag two_attr_done;
+    if (!two_attr_done.get()) {
+      e = cudaFuncSetAttribute(k_gemm_tc<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      two_attr_done.set();
+    }
+    if (e == cudaSuccess) e = launch(k_gemm_tc<2, false, true>, 320);
   } else {
     if (!attr_done[2].get()) {
       e = cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
