@@ -56,17 +56,14 @@ def test_pointwise_gemm(precision, rel_tol, K, N, hw, n):
 
 @pytest.mark.parametrize('K,N,hw,n', [(512, 512, 19, 4), (1024, 1024, 10, 8), (256, 48, 3, 1), (64, 128, 20, 3)])
 def test_tmem_staged_a_operand(monkeypatch, K, N, hw, n):
-    """Experimental WB_TMEM_A=1 path of k_gemm_tc<2, true>: the converter warps tcgen05.st the hi / lo rows into
+    """The TMEM-staged A operand of k_gemm_tc<2, true> (default; WB_TMEM_A=0 = shared-memory hi / lo tiles): the converter warps tcgen05.st the hi / lo rows into
     tensor memory and the MMAs take A from there.  Same bar as the shared-memory path; where both use one main
     accumulator (chains <= 16 steps) the two must agree bit for bit."""
     m, w1, sc, of = tiny_model(K, N, hw)
     pre = np.random.default_rng(1).standard_normal((n, hw, hw, 3)).astype(np.float32)
     out = {}
     for ta in (False, True):
-        if ta:
-            monkeypatch.setenv('WB_TMEM_A', '1')
-        else:
-            monkeypatch.delenv('WB_TMEM_A', raising=False)
+        monkeypatch.setenv('WB_TMEM_A', '1' if ta else '0')
         with Engine(m.to_blob(), device=0, max_batch=n, precision=2) as e:
             _, _, a = e.backbone(pre, stop_layer=0, layer_shape=(hw, hw, K))
             _, _, out[ta] = e.backbone(pre, stop_layer=1, layer_shape=(hw, hw, N))

@@ -134,7 +134,7 @@ __device__ __forceinline__ void copy_out_row(const TcArgs& g, const uint8_t* sme
 }
 
 // MODE 0: bf16 operands; MODE 1: tf32 single product (diagnostic); MODE 2: tf32 x3 split
-// TA (TF32X3 only, experimental, WB_TMEM_A=1): the converter warps write the hi / lo rows into tensor memory
+// TA (TF32X3 only; default, WB_TMEM_A=0 disables): the converter warps write the hi / lo rows into tensor memory
 // (tcgen05.st) and the MMAs take A from there, so the shared-memory port carries neither the converter writes
 // nor the A operand reads.
 // TWO: compiled for two co-resident CTAs per SM (<= 102 registers; the launcher keeps shared memory <= 110 KB and
@@ -1069,10 +1069,13 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       // accumulator halves the TMEM footprint, so two such CTAs can share an SM
       if (g.kb_per * (ROW_BYTES / UMMA_K_BYTES) <= 16) g.n_main = 1;
     }
-    if (mode == TC_TF32X3 && !g.conv && getenv("WB_TMEM_A") != nullptr) {
-      // experimental: A ring in tensor memory; chains of <= 32 steps per main accumulator
+    const char* ta_env = getenv("WB_TMEM_A");
+    if (mode == TC_TF32X3 && !g.conv && !(ta_env != nullptr && ta_env[0] == '0')) {
+      // A operand of the 3xTF32 MMAs from tensor memory (default since round 2: +3.3 % on the v2 step; WB_TMEM_A=0
+      // switches back to the shared-memory hi / lo tiles)
+      // A ring in tensor memory; chains of <= 32 steps per main accumulator
       const int steps = g.kb_per * (ROW_BYTES / UMMA_K_BYTES);
-      const int nm = steps <= 32 ? 1 : (steps <= 64 ? 2 : 3);
+      const int nm = steps <= 16 ? 1 : (steps <= 48 ? 2 : 3);  // same rotation rule as the shared-memory path
       const int ta = std::min(4, (512 - (nm + 1) * g.block_n) / 64);
       if (ta >= 2) {
         g.n_main = nm;
