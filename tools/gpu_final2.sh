@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 evidence in one gpurun call: default bench line, the CPU reference arm, the Inception line, the ncu launch
+# list, a --set full capture of one step's tcgen05 launches, smoke.  Logs -> gpurun_out/ (copied to profiles/ by hand).
+mkdir -p gpurun_out
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_smoke.log
+echo "== bench (default)"
+timeout 900 python bench.py 2> gpurun_out/r02_bench.err | tail -1 > gpurun_out/r02_bench_line.json; cut -c1-300 gpurun_out/r02_bench_line.json
+echo "== bench --steps 20 --warmup 5 (the driver's length)"
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-worker --no-real-weights 2>/dev/null | tail -1 > gpurun_out/r02_bench_k20.json; cut -c1-200 gpurun_out/r02_bench_k20.json
+echo "== bench --impl reference"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_reference_line.json; cut -c1-300 gpurun_out/r02_bench_reference_line.json
+echo "== bench --model inception --cameras 2 (configs[4] per GPU)"
+timeout 600 python bench.py --model inception --cameras 2 --steps 200 --warmup 10 --no-worker 2>/dev/null | tail -1 > gpurun_out/r02_bench_inception.json; cut -c1-300 gpurun_out/r02_bench_inception.json
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
+    --log-file gpurun_out/launches_r02.csv python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_list.log 2>&1
+tail -1 gpurun_out/r02_ncu_list.log | cut -c1-120
+echo "== ncu --set full (one step of tcgen05 launches)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gemm_tc|k_dwpw|k_irb' -s 300 -c 52 \
+    -o gpurun_out/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
+tail -1 gpurun_out/r02_ncu_full.log | cut -c1-120
+ls -la gpurun_out/prof_r02.ncu-rep gpurun_out/launches_r02.csv

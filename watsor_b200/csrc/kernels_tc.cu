@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   float* s_so = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [2][n_pad]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = g.n_pad / g.block_n;
+  const int n_tiles = (g.n_pad + g.block_n - 1) / g.block_n;  // the last N tile may be ragged (N = 144 = 128 + 16)
+  const int nt_cols = n_tiles * g.block_n;
   const int num_tiles = ((g.M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
   const int n_acc = X3 ? g.n_main + 1 : 1;
   const int set_cols = n_acc * g.block_n;
@@ -591,9 +592,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
-  for (int i = threadIdx.x; i < g.n_pad; i += blockDim.x) {
-    s_so[i] = g.scale[i];
-    s_so[g.n_pad + i] = g.offset[i];
+  for (int i = threadIdx.x; i < nt_cols; i += blockDim.x) {
+    s_so[i] = i < g.n_pad ? g.scale[i] : 1.f;
+    s_so[nt_cols + i] = i < g.n_pad ? g.offset[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -667,7 +668,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
-      for (int c0 = 0; c0 < g.block_n; c0 += CW, ++chunk_no) {
+      for (int c0 = 0; c0 < g.block_n; c0 += CW) {
+        if (n0 + c0 >= g.N) break;  // ragged last N tile: these columns do not exist
         float y[CW];
 #pragma unroll
         for (int h = 0; h < CW / 32; ++h) {
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const int nn = n0 + c0 + h * 32 + i;
-            const float4 sc = lds128_ro(smem_u32(s_so + nn)), of = lds128_ro(smem_u32(s_so + g.n_pad + nn));
+            const float4 sc = lds128_ro(smem_u32(s_so + nn)), of = lds128_ro(smem_u32(s_so + nt_cols + nn));
             const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, ofs[4] = {of.x, of.y, of.z, of.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -727,6 +729,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
           tma_store_2d(&map_out, smem_u32(my_stage + (size_t)(chunk_no & 1) * 4096), n0 + c0, m0 + q * 32);
           bulk_commit();
         }
+        ++chunk_no;
       }
       // every TMEM read of this tile has completed: hand the accumulator set back to the MMA warp
       tc_fence_before();
@@ -1048,8 +1051,17 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  bool persist = !g.is_head && !g.conv && g.splits == 1 && tiles >= num_sms && (g.N == g.n_pad || (g.N % 4 == 0 && mode != TC_BF16)) && g.block_n % cw == 0 &&
-                 g.n_pad % g.block_n == 0 && getenv("WB_NO_PERSIST") == nullptr;
+  // N = 144 (one 144-wide UMMA tile: 2 x 2 x 144 TMEM columns do not fit twice) runs persistent as 128 + a ragged 16:
+  // the weight rows beyond N are zero-filled by TMA and the missing output columns are skipped / clipped.
+  if (mode == TC_TF32X3 && !g.is_head && !g.conv && g.block_n > 128 && g.block_n == g.n_pad && g.N % 4 == 0 &&
+      (long)grid.x * ((g.n_pad + 127) / 128) >= num_sms && getenv("WB_NO_RAGGED_N") == nullptr) {
+    g.block_n = 128;
+    grid.y = (g.n_pad + 127) / 128;
+    stage_bytes = A_TILE_BYTES * x3 + g.block_n * ROW_BYTES * x3;
+  }
+  const long ptiles = (long)grid.x * grid.y;
+  bool persist = !g.is_head && !g.conv && g.splits == 1 && ptiles >= num_sms && (g.N == g.n_pad || (g.N % 4 == 0 && mode != TC_BF16)) && g.block_n % cw == 0 &&
+                 (g.n_pad % g.block_n == 0 || mode == TC_TF32X3) && getenv("WB_NO_PERSIST") == nullptr;
   if (persist && mode == TC_TF32X3) {
     g.n_main = std::max(1, std::min(3, 512 / (2 * g.block_n) - 1));
     if (g.k_blocks * (ROW_BYTES / UMMA_K_BYTES) <= 32) g.n_main = 1;  // short chains: no measurable bias
@@ -1058,7 +1070,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   if (persist && mode != TC_TF32X3 && 2 * g.block_n > 512) persist = false;
   int stages;
   if (persist) {
-    stages = (224 * 1024 - STAGING_BYTES - 8 * g.n_pad) / stage_bytes;
+    stages = (224 * 1024 - STAGING_BYTES - 8 * (int)(grid.y * g.block_n)) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) persist = false;
   }
@@ -1075,7 +1087,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       // switches back to the shared-memory hi / lo tiles)
       // A ring in tensor memory; chains of <= 32 steps per main accumulator
       const int steps = g.kb_per * (ROW_BYTES / UMMA_K_BYTES);
-      const int nm = steps <= 16 ? 1 : (steps <= 48 ? 2 : 3);  // same rotation rule as the shared-memory path
+      const int nm = steps <= 16 ? 1 : (steps <= 24 ? 2 : 3);  // chains > 24 MMAs rotate over 3 accumulators (layer-by-layer bar)
       const int ta = std::min(4, (512 - (nm + 1) * g.block_n) / 64);
       if (ta >= 2) {
         g.n_main = nm;
@@ -1105,7 +1117,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     const int staging = BLOCK_M * (g.block_n + 4) * 4;  // epilogue staging tile re-uses the stage ring
     g.ring_bytes = ((std::max(g.ring_bytes, staging) + 1023) / 1024) * 1024;
   }
-  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES + 8 * (size_t)g.n_pad + 32 : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
+  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES + 8 * (size_t)(grid.y * g.block_n) + 32 : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
   alignas(64) CUtensorMap map_a;
   if (g.conv) {
     const int imgs = BLOCK_M / (int)(L.out_h * L.out_w);
@@ -1160,7 +1172,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       persist_ctas = e ? atoi(e) : num_sms;
       if (persist_ctas <= 0 || persist_ctas > num_sms) persist_ctas = num_sms;
     }
-    dim3 pgrid((unsigned)std::min<long>(tiles, persist_ctas));
+    dim3 pgrid((unsigned)std::min<long>(ptiles, persist_ctas));
     if (mode == TC_BF16) {
       if (!attr_done[idx].get()) e = cudaFuncSetAttribute(k_gemm_tc_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       k_gemm_tc_persist<0><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
