@@ -7,7 +7,13 @@ polygons each zone becomes a filled-contour raster; libwatsor_b200 turns the ras
 summed-area tables in HBM, and "bounding box intersects zone polygon" (mask.py:54) becomes
 "the box covers at least one raster pixel" -- 4 loads per (detection, zone).  Both are the
 same predicate because contour vertices are pixel centres joined by 8-connected unit steps
-(DESIGN.md, tests/test_mask_equivalence.py).
+(DESIGN.md section 5; tests/test_oracle_filters.py::test_raster_sat_equals_exact_polygon_intersection checks the raster /
+summed-area form against exact integer geometry on porch.png and random masks with holes and islands, including
+zero-width / zero-height boxes).  Not covered: GEOS' treatment of invalid self-touching rings from 1-pixel-wide zones
+(shapely is not installable here).  One visible difference from the reference: the fused detector path
+(`WB_F_FUSE_FILTERS`) clears `zones[]` of every row before judging it, whereas `TensorFlowObjectDetector.detect`
+never touches zones (ref:tensorflow_cpu.py:79-90; the reference's sieve works on a zeroed clone, sieve.py:24-27, so
+the published rows agree).
 """
 import cv2
 import numpy as np
