@@ -16,8 +16,10 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
     --log-file gpurun_out/launches_r02.csv python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_list.log 2>&1
 tail -1 gpurun_out/r02_ncu_list.log | cut -c1-120
-echo "== ncu --set full (one step of tcgen05 launches)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gemm_tc|k_dwpw|k_irb' -s 300 -c 52 \
-    -o gpurun_out/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
+echo "== ncu --set full (one step of tcgen05 launches; the report stays on the box, its raw page comes back as CSV)"
+timeout 900 ncu --set full --clock-control none -k regex:'k_gemm_tc|k_dwpw|k_irb' -s 300 -c 48 \
+    -o /tmp/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
 tail -1 gpurun_out/r02_ncu_full.log | cut -c1-120
-ls -la gpurun_out/prof_r02.ncu-rep gpurun_out/launches_r02.csv
+ncu -i /tmp/prof_r02.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
+ls -la /tmp/prof_r02.ncu-rep gpurun_out/r02_ncu_full_raw.csv gpurun_out/launches_r02.csv
+du -sh gpurun_out

@@ -543,10 +543,10 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, TWO ? 2 : 1)
 // across tiles, the TMEM accumulators are double-buffered (the epilogue of tile j overlaps the TMA /
 // convert / MMA work of tile j+1) and the epilogue leaves through 128B-swizzled staging buffers and
 // TMA stores (cp.async.bulk.tensor ... global.shared::cta), i.e. fully coalesced 128-byte rows.
-constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B); 3xTF32: 8 warps, twice that
 
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
+__global__ void __launch_bounds__(MODE == 2 ? 448 : 192, 1)
     k_gemm_tc_persist(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
                       TcArgs g) {
@@ -555,12 +555,16 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
   constexpr int ELEM = TF32 ? 4 : 2;
   constexpr int K_PER_BLOCK = ROW_BYTES / ELEM;
   constexpr int CW = TF32 ? 32 : 64;  // output columns per 128-byte staging row
+  // 3xTF32: a second group of four epilogue warps (warps 10..13; TMEM lane quarter = warp % 4 as for warps 2..5) takes
+  // every second column chunk -- the epilogue is bound by instruction latency (one warp per scheduler), not bandwidth
+  constexpr int EPI_WARPS = X3 ? 8 : 4;
+  constexpr int STAGING = EPI_WARPS * 2 * 4096;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = g.block_n * ROW_BYTES;
   const int stage_bytes = A_TILE_BYTES * (X3 ? 2 : 1) + b_tile_bytes * (X3 ? 2 : 1);
   uint8_t* staging = smem + (size_t)g.stages * stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STAGING);
   uint64_t* empty = full + g.stages;
   uint64_t* conv = empty + g.stages;
   uint64_t* acc_full = conv + g.stages;  // [2]
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc_full[b]), 1);
-      mbar_init(smem_u32(&acc_empty[b]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&acc_empty[b]), EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -657,9 +661,10 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 || warp >= 10) {
     const int q = warp & 3;
-    uint8_t* my_stage = staging + (size_t)q * 2 * 4096;
+    const int grp = warp >= 10 ? 1 : 0;
+    uint8_t* my_stage = staging + (size_t)(grp * 4 + q) * 2 * 4096;
     const int used = X3 ? min(g.n_main, g.k_blocks * (ROW_BYTES / UMMA_K_BYTES)) : 1;
     int j = 0, chunk_no = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++j) {
@@ -668,8 +673,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 320 : 192, 1)
       mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * set_cols);
-      for (int c0 = 0; c0 < g.block_n; c0 += CW) {
+      for (int c0 = 0, ci = 0; c0 < g.block_n; c0 += CW, ++ci) {
         if (n0 + c0 >= g.N) break;  // ragged last N tile: these columns do not exist
+        if (EPI_WARPS == 8 && (ci & 1) != grp) continue;
         float y[CW];
 #pragma unroll
         for (int h = 0; h < CW / 32; ++h) {
@@ -1070,7 +1076,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
   if (persist && mode != TC_TF32X3 && 2 * g.block_n > 512) persist = false;
   int stages;
   if (persist) {
-    stages = (224 * 1024 - STAGING_BYTES - 8 * (int)(grid.y * g.block_n)) / stage_bytes;
+    stages = (224 * 1024 - STAGING_BYTES * (mode == TC_TF32X3 ? 2 : 1) - 8 * (int)(grid.y * g.block_n)) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) persist = false;
   }
@@ -1117,7 +1123,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
     const int staging = BLOCK_M * (g.block_n + 4) * 4;  // epilogue staging tile re-uses the stage ring
     g.ring_bytes = ((std::max(g.ring_bytes, staging) + 1023) / 1024) * 1024;
   }
-  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES + 8 * (size_t)(grid.y * g.block_n) + 32 : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
+  const size_t smem = (size_t)g.ring_bytes + (persist ? STAGING_BYTES * (mode == TC_TF32X3 ? 2 : 1) + 8 * (size_t)(grid.y * g.block_n) + 32 : 0) + 1024 /*align*/ + 8 * (3 * stages + 4) + 16 + 64 /*TA barriers*/;
   alignas(64) CUtensorMap map_a;
   if (g.conv) {
     const int imgs = BLOCK_M / (int)(L.out_h * L.out_w);
@@ -1181,7 +1187,7 @@ int tc_launch_gemm(const LaunchCtx& lc, const TcWeights& tw, int layer_index, in
       k_gemm_tc_persist<1><<<pgrid, 192, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
     } else {
       if (!attr_done[idx].get()) e = cudaFuncSetAttribute(k_gemm_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      k_gemm_tc_persist<2><<<pgrid, 320, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
+      k_gemm_tc_persist<2><<<pgrid, 448, smem, lc.stream>>>(map_a, map_b, map_b_lo, map_out, g);
     }
     attr_done[idx].set();
   } else if (mode == TC_BF16) {
