@@ -2,6 +2,16 @@
 # Round-2 evidence in one gpurun call: default bench line, the CPU reference arm, the Inception line, the ncu launch
 # list, a --set full capture of one step's tcgen05 launches, smoke.  Logs -> gpurun_out/ (copied to profiles/ by hand).
 mkdir -p gpurun_out
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu --maxfail=8 -q -s --timeout 400 --timeout-method=thread 2>&1 | tail -150 > gpurun_out/r02_pytest.log
+grep -E "passed|failed|FAILED" gpurun_out/r02_pytest.log | tail -8
+if grep -qE "^FAILED|^ERROR|[0-9]+ failed|[0-9]+ error" gpurun_out/r02_pytest.log; then
+  # the evidence below must describe a parity-green build: fall back to the direct (unstaged) stem and say so
+  export WB_NO_STAGE=1
+  echo "TESTS FAILED -> WB_NO_STAGE=1 for the evidence" | tee gpurun_out/r02_fallback.txt
+  timeout 900 python -m pytest tests -m gpu --maxfail=8 -q --timeout 400 --timeout-method=thread 2>&1 | tail -30 > gpurun_out/r02_pytest_nostage.log
+  grep -E "passed|failed|FAILED" gpurun_out/r02_pytest_nostage.log | tail -8
+fi
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r02_smoke.log
 echo "== bench (default)"
@@ -21,5 +31,18 @@ timeout 900 ncu --set full --clock-control none -k regex:'k_gemm_tc|k_dwpw|k_irb
     -o /tmp/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
 tail -1 gpurun_out/r02_ncu_full.log | cut -c1-120
 ncu -i /tmp/prof_r02.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
+echo "== stem / resize kernels: time + DRAM bytes (640x480 bench, 1920x1080 inception bench, stand-alone kernel)"
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640.csv \
+    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > /dev/null 2>&1
+timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_1080.csv \
+    python bench.py --model inception --cameras 2 --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-worker --min-seconds 0 > /dev/null 2>&1
+timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess.csv \
+    python tools/pre_probe.py > gpurun_out/r02_pre_probe.log 2>&1
+WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640_nostage.csv \
+    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > /dev/null 2>&1
+WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess_nostage.csv \
+    python tools/pre_probe.py > /dev/null 2>&1
+grep -h "gpu__time" gpurun_out/r02_stem_640.csv gpurun_out/r02_stem_640_nostage.csv gpurun_out/r02_stem_1080.csv gpurun_out/r02_preprocess.csv gpurun_out/r02_preprocess_nostage.csv | cut -d, -f5,13- | head -30
 ls -la /tmp/prof_r02.ncu-rep gpurun_out/r02_ncu_full_raw.csv gpurun_out/launches_r02.csv
 du -sh gpurun_out

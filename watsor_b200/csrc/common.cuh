@@ -99,11 +99,13 @@ struct LaunchCtx {
 };
 
 void launch_preprocess_f32(const LaunchCtx& lc, const FrameDesc* frames, int n, float* out, int oh, int ow,
-                           float mul, float sub);
+                           float mul, float sub, int max_src_w);
+// max_src_w: widest source frame the launch may see (sizes the shared-memory staging of source rows; frames that do
+// not fit take the direct path inside the kernel); 0 = never stage
 template <typename T>
 void launch_stem(const LaunchCtx& lc, const FrameDesc* frames, const float* pre, int n, const wb_layer& L,
                  int in_h, int in_w, float mul, float sub, const float* w, const float* scale,
-                 const float* offset, T* out);
+                 const float* offset, T* out, int max_src_w);
 template <typename T>
 void launch_dw(const LaunchCtx& lc, int n, const wb_layer& L, const T* in, const float* w, const float* scale,
                const float* offset, T* out);

@@ -60,6 +60,7 @@ struct Slot {
   cudaGraphExec_t graph_exec = nullptr;
   int graph_n = -1;
   uint32_t graph_flags = 0;
+  int graph_src_w = 0;  // widest camera the captured stem kernel sized its staging for
 };
 
 struct wb_ctx {
@@ -67,6 +68,7 @@ struct wb_ctx {
   int max_batch = 0;
   int precision = 0;
   bool use_graph = true;
+  int max_src_w = 0;  // widest configured camera: sizes the stem's shared-memory staging of source rows
   cudaDeviceProp prop;
   wb_model_header hdr;
   std::vector<wb_layer> layers;
@@ -333,6 +335,7 @@ int wb_set_camera(wb_ctx* c, int cam, int width, int height, int n_zones, const 
   memset(&cfg, 0, sizeof(cfg));
   cfg.width = width;
   cfg.height = height;
+  c->max_src_w = std::max(c->max_src_w, width);
   cfg.n_zones = n_zones;
   cfg.has_mask = raster != nullptr ? 1 : 0;
   cfg.check_label = (cam_flags & WB_CAM_NO_LABEL_CHECK) ? 0 : 1;
@@ -439,7 +442,7 @@ static int run_layers(wb_ctx* c, Slot& s, cudaStream_t st, int n, const float* p
     switch (L.op) {
       case WB_OP_STEM:
         launch_stem<T>(lc, s.d_desc, pre, n, L, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub, w,
-                       sc, of, outp);
+                       sc, of, outp, c->max_src_w);
         break;
       case WB_OP_DW: {
         // depthwise -> 1x1 pairs run as one tensor-core kernel when both layers are in the requested range
@@ -550,7 +553,7 @@ static int enqueue_kernels(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t 
     s.launches = 0;
     return run_all(c, s, st, n, gflags);
   }
-  if (s.graph_exec == nullptr || s.graph_n != n || s.graph_flags != gflags) {
+  if (s.graph_exec == nullptr || s.graph_n != n || s.graph_flags != gflags || s.graph_src_w != c->max_src_w) {
     if (s.graph_exec) {
       cudaGraphExecDestroy(s.graph_exec);
       s.graph_exec = nullptr;
@@ -570,6 +573,7 @@ static int enqueue_kernels(wb_ctx* c, Slot& s, cudaStream_t st, int n, uint32_t 
     CK(cudaGraphDestroy(graph));
     s.graph_n = n;
     s.graph_flags = gflags;
+    s.graph_src_w = c->max_src_w;
   }
   CK(cudaGraphLaunch(s.graph_exec, st));
   return 0;
@@ -729,7 +733,10 @@ int wb_preprocess(wb_ctx* c, int n, const uint8_t* const* frames, const int32_t*
   }
   CK(cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, st));
   LaunchCtx lc{st, &s.launches};
-  launch_preprocess_f32(lc, s.d_desc, n, s.d_pre, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub);
+  int max_w = 0;
+  for (int i = 0; i < n; ++i) max_w = std::max(max_w, (int)widths[i]);
+  launch_preprocess_f32(lc, s.d_desc, n, s.d_pre, c->hdr.input_h, c->hdr.input_w, c->hdr.pre_mul, c->hdr.pre_sub,
+                        max_w);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, s.d_pre, sizeof(float) * (size_t)n * c->hdr.input_h * c->hdr.input_w * 3,
                      cudaMemcpyDeviceToHost, st));
