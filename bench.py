@@ -63,6 +63,9 @@ def parse_args():
     p.add_argument('--no-roofline', action='store_true')
     p.add_argument('--no-real-weights', action='store_true', help='skip the second (real-weights v1) record')
     p.add_argument('--no-scatter', action='store_true', help='skip the NCCL scatter record at N>1')
+    p.add_argument('--scatter-impl', default='cabi', choices=['cabi', 'torch'],
+                   help="cabi: the library's own communicator (wb_comm_init / wb_scatter_frames); torch: "
+                        'torch.distributed.scatter')
     p.add_argument('--no-worker', action='store_true', help='skip the e2e_worker record')
     p.add_argument('--min-seconds', type=float, default=1.0,
                    help='the *_long / e2e measurements run at least this long')
@@ -317,6 +320,7 @@ class Arm:
         self.stream = torch.cuda.Stream()
         self.scatter_buf = None
         self.scatter_events = []
+        self.comm_ready = False
 
     def close(self):
         self.det.engine.close()
@@ -337,9 +341,19 @@ class Arm:
         self.scatter_buf = [torch.empty((self.C, H, W, 3), dtype=torch.uint8, device='cuda') for _ in range(self.NS)]
         if self.rank == 0:
             self.all_ring = [self.dev_ring.clone() for _ in range(self.world)]
+        if self.args.scatter_impl == 'cabi' and not self.comm_ready:
+            from watsor_b200.parallel import init_engine_comm
+            init_engine_comm(self.det.engine, self.rank, self.world)
+            self.comm_ready = True
 
     def dev_ptrs(self, step, slot, time_scatter=False):
-        from watsor_b200.parallel import scatter_frames
+        from watsor_b200.parallel import engine_scatter_frames
+        from watsor_b200.parallel import scatter_frames as torch_scatter_frames
+        if self.args.scatter_impl == 'cabi':
+            def scatter_frames(recv, per_rank, src=0):
+                engine_scatter_frames(self.det.engine, recv, per_rank, root=src, cuda_stream=self.stream.cuda_stream)
+        else:
+            scatter_frames = torch_scatter_frames
         r = step % self.ring
         if self.scatter_buf is not None:
             # the engine's frame scatter: rank 0 owns every camera's frame and NCCL-scatters each rank's
@@ -463,8 +477,10 @@ class Arm:
                'nvlink_bytes_per_tick': (world - 1) * C * self.frame_bytes,
                'scatter_us_median': float(np.median(us)) if us else None,
                'scatter_us_p90': float(np.percentile(us, 90)) if us else None,
-               'collective': 'torch.distributed.scatter (ncclScatter: grouped send/recv) of [C,H,W,3] u8 per rank '
-                             'from rank 0; the kernels read the receive buffer in place'}
+               'collective': ('wb_scatter_frames (C-ABI; grouped ncclSend/ncclRecv on the library\'s own communicator)'
+                              if args.scatter_impl == 'cabi' else
+                              'torch.distributed.scatter (ncclScatter: grouped send/recv)') +
+                             ' of [C,H,W,3] u8 per rank from rank 0; the kernels read the receive buffer in place'}
         self.scatter_buf = None
         return rec
 

@@ -134,6 +134,26 @@ int wb_collect(wb_ctx* ctx, int slot, wb_detection* const* out, uint32_t* const*
  * Lets a caller bracket several in-flight wb_submit() batches with its own CUDA events. */
 int wb_stream_fence(wb_ctx* ctx, uint64_t cuda_stream, int direction);
 
+/* ---- engine frame scatter (BASELINE.json north star: "NCCL over NVLink only for the engine's frame scatter";
+ * SURVEY.md section 8(b)/(e)).  The reference has no counterpart: its detectors pull frames from one queue
+ * (detector.py:40-50).  One rank (the ingest rank) owns a tick's frames of every camera and sends each rank its slab;
+ * the detection kernels read the receive buffer in place (wb_submit with WB_F_FRAMES_ON_DEVICE).
+ * NCCL is bound at run time -- the libnccl.so.2 already loaded in the process, else the file WB_NCCL_LIB names, else
+ * the system one; the library has no link-time dependency on it and every other entry point works without it.
+ *   wb_comm_unique_id : rank `root` makes the 128-byte rendezvous id; ship it to the other ranks over any host channel
+ *   wb_comm_init      : collective over the `world` contexts (one per process / GPU)
+ *   wb_scatter_frames : root: send_per_rank[r] = device pointer of rank r's slab (bytes_per_rank bytes each; the
+ *                       root's own slab is a device copy); other ranks pass NULL.  recv = this rank's device buffer.
+ *                       cuda_stream = 0: runs on the context's communication stream and every later wb_submit on
+ *                       this context is ordered after it; otherwise it is enqueued on the caller's stream (order the
+ *                       slots with wb_stream_fence).  The caller guarantees that nothing still reads `recv`. */
+#define WB_COMM_ID_BYTES 128
+int wb_comm_unique_id(uint8_t* id_out);
+int wb_comm_init(wb_ctx* ctx, int rank, int world, const uint8_t* id);
+int wb_scatter_frames(wb_ctx* ctx, int root, const uint8_t* const* send_per_rank, uint8_t* recv,
+                      size_t bytes_per_rank, uint64_t cuda_stream);
+int wb_comm_destroy(wb_ctx* ctx);
+
 /* ---- stage-level entry points (parity tests call the same kernels stage by stage) -------------- */
 /* graph nodes Cast + Preprocessor/... : out = float32 [n][in_h][in_w][3] on the host */
 int wb_preprocess(wb_ctx* ctx, int n, const uint8_t* const* frames, const int32_t* widths,

@@ -30,7 +30,7 @@ def worker(rank, world, port, out):
     from tests.gpu_util import new_rows, rows_bytes
     from watsor_b200.detection.b200 import B200ObjectDetector
     from watsor_b200.model import Model
-    from watsor_b200.parallel import camera_shard, scatter_frames
+    from watsor_b200.parallel import camera_shard, engine_scatter_frames, init_engine_comm, scatter_frames
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
@@ -55,6 +55,26 @@ def worker(rank, world, port, out):
         det.detect_batch([mine[c] for c in range(C)], list(range(C)), b, fuse_filters=False)
         same_rows = all(rows_bytes(x) == rows_bytes(y) for x, y in zip(a, b))
         found = sum(1 for rows in a for r in range(100) if rows[r].confidence > 0.5)
+        # the same scatter through the C-ABI's own communicator (wb_comm_init / wb_scatter_frames): a second tick's
+        # frames land in a fresh buffer and the batch submitted right after it is ordered behind the transfer
+        init_engine_comm(det.engine, rank, world)
+        mine2 = np.stack([artist_frame(W, H, g, 1) for g in cams])
+        per_rank2 = None
+        if rank == 0:
+            per_rank2 = [torch.from_numpy(np.stack([artist_frame(W, H, g, 1) for g in camera_shard(r, world, C)])).cuda()
+                         for r in range(world)]
+        recv2 = torch.zeros((C, H, W, 3), dtype=torch.uint8, device='cuda')
+        torch.cuda.synchronize()
+        c_rows, d_rows = new_rows(C), new_rows(C)
+        for _ in range(3):      # repeated ticks re-use the communicator and the receive buffer
+            engine_scatter_frames(det.engine, recv2, per_rank2, root=0)
+            det.detect_batch([recv2[c].data_ptr() for c in range(C)], list(range(C)), c_rows, fuse_filters=False,
+                             frames_on_device=True)
+        det.detect_batch([mine2[c] for c in range(C)], list(range(C)), d_rows, fuse_filters=False)
+        torch.cuda.synchronize()
+        same_bytes = same_bytes and bool((recv2.cpu().numpy() == mine2).all())
+        same_rows = same_rows and all(rows_bytes(x) == rows_bytes(y) for x, y in zip(c_rows, d_rows))
+        det.engine.comm_destroy()
     dist.barrier()
     out.put((rank, same_bytes, same_rows, found))
     dist.destroy_process_group()

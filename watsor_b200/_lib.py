@@ -25,6 +25,20 @@ class WatsorB200Error(RuntimeError):
 _lib = None
 
 
+def _point_at_bundled_nccl():
+    """`wb_comm_*` binds NCCL with dlopen.  If no copy is loaded yet, make it pick the one PyTorch ships
+    (site-packages/nvidia/nccl/lib/libnccl.so.2) rather than a different system version with the same SONAME,
+    after which `import torch` would fail to resolve its symbols.  No import of torch or nvidia.* happens here."""
+    if os.environ.get('WB_NCCL_LIB'):
+        return
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, 'nvidia', 'nccl', 'lib', 'libnccl.so.2')
+        if base and os.path.isfile(cand):
+            os.environ['WB_NCCL_LIB'] = cand
+            return
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -34,6 +48,7 @@ def load():
             'libwatsor_b200.so is not built (%s). Build it with '
             '`python -c "import __graft_entry__ as g; g.build()"` or `make -C watsor_b200/csrc`. '
             'There is no CPU fallback.' % LIB_PATH)
+    _point_at_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH)
     P = POINTER
     sig = {
@@ -54,6 +69,10 @@ def load():
         'wb_submit': (c_int, [c_void_p, c_int, c_int, P(c_void_p), P(c_int32), c_uint32]),
         'wb_collect': (c_int, [c_void_p, c_int, P(c_void_p), P(c_void_p), P(c_float)]),
         'wb_stream_fence': (c_int, [c_void_p, c_uint64, c_int]),
+        'wb_comm_unique_id': (c_int, [c_void_p]),
+        'wb_comm_init': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+        'wb_scatter_frames': (c_int, [c_void_p, c_int, P(c_void_p), c_void_p, c_size_t, c_uint64]),
+        'wb_comm_destroy': (c_int, [c_void_p]),
         'wb_preprocess': (c_int, [c_void_p, c_int, P(c_void_p), P(c_int32), P(c_int32), c_void_p]),
         'wb_backbone': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t]),
         'wb_postprocess': (c_int, [c_void_p, c_int, c_void_p, c_void_p, P(c_int32), c_uint32,
@@ -83,7 +102,8 @@ def load():
 
 EXPORTS = ['wb_abi_version', 'wb_last_error', 'wb_device_count', 'wb_create', 'wb_destroy',
            'wb_device_name', 'wb_set_stream', 'wb_model_info', 'wb_set_camera', 'wb_register_host',
-           'wb_unregister_host', 'wb_detect', 'wb_submit', 'wb_collect', 'wb_stream_fence', 'wb_preprocess', 'wb_backbone',
+           'wb_unregister_host', 'wb_detect', 'wb_submit', 'wb_collect', 'wb_stream_fence', 'wb_comm_unique_id', 'wb_comm_init',
+           'wb_scatter_frames', 'wb_comm_destroy', 'wb_preprocess', 'wb_backbone',
            'wb_postprocess', 'wb_filter_rows', 'wb_anchors', 'wb_last_launch_count', 'wb_profile_layers',
            'wb_tracker_create', 'wb_tracker_destroy', 'wb_tracker_update', 'wb_sieve_rows', 'wb_debug_pyset_order',
            'wb_debug_unused_order', 'wb_debug_argsort']

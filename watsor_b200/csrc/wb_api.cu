@@ -1,6 +1,9 @@
 // wb_api.cu -- the C-ABI of libwatsor_b200.so (include/watsor_b200.h): context, model upload,
 // per-camera filter state, the layer-program executor, two-slot asynchronous pipeline and the
 // stage-level entry points the parity tests use.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the functions are bound with dlopen in wb_comm_*
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +72,11 @@ struct wb_ctx {
   int precision = 0;
   bool use_graph = true;
   int max_src_w = 0;  // widest configured camera: sizes the stem's shared-memory staging of source rows
+  // frame scatter (wb_comm_*): NCCL communicator bound at run time, its stream and the event the slots wait on
+  void* comm = nullptr;
+  int comm_rank = -1, comm_world = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev = nullptr;
   cudaDeviceProp prop;
   wb_model_header hdr;
   std::vector<wb_layer> layers;
@@ -246,6 +254,7 @@ int wb_destroy(wb_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  wb_comm_destroy(c);
   for (void* r : c->registered) cudaHostUnregister(r);
   for (auto& s : c->slots) {
     if (s.graph_exec) cudaGraphExecDestroy(s.graph_exec);
@@ -937,3 +946,147 @@ int wb_profile_layers(wb_ctx* c, int n, const uint8_t* const* device_frames, con
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Engine frame scatter over NCCL, bound with dlopen so that the library itself does not depend on libnccl.
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // one NCCL per process: the copy that is already loaded wins (torch brings its own libnccl.so.2 and cannot be
+    // imported after a different one -- same SONAME); then WB_NCCL_LIB (the Python shim points it at the copy bundled
+    // with torch, so a later `import torch` still works); then the system library
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    const char* override_path = getenv("WB_NCCL_LIB");
+    if (!api.handle && override_path && override_path[0]) api.handle = dlopen(override_path, RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) {
+      const char* e = dlerror();
+      api.error = std::string("cannot load NCCL (libnccl.so.2): ") + (e ? e : "not found");
+      return;
+    }
+    bool ok = true;
+    auto sym = [&](const char* name) {
+      void* p = dlsym(api.handle, name);
+      if (!p) {
+        ok = false;
+        api.error = std::string("NCCL symbol missing: ") + name;
+      }
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) api.handle = nullptr;
+  });
+  return &api;
+}
+}  // namespace
+
+#define NCCL_CK(api, call)                                                                      \
+  do {                                                                                          \
+    ncclResult_t _r = (call);                                                                   \
+    if (_r != ncclSuccess) return fail(std::string(#call) + ": " + (api)->GetErrorString(_r));  \
+  } while (0)
+
+static_assert(sizeof(ncclUniqueId) == WB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+
+int wb_comm_unique_id(uint8_t* id_out) {
+  REQUIRE(id_out, "NULL id_out");
+  NcclApi* api = nccl_api();
+  if (!api->handle) return fail(api->error);
+  ncclUniqueId id;
+  NCCL_CK(api, api->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int wb_comm_init(wb_ctx* c, int rank, int world, const uint8_t* id_bytes) {
+  REQUIRE(c, "NULL ctx");
+  REQUIRE(id_bytes, "NULL id");
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank must be in [0, world)");
+  NcclApi* api = nccl_api();
+  if (!api->handle) return fail(api->error);
+  std::lock_guard<std::mutex> lock(c->mu);
+  REQUIRE(c->comm == nullptr, "the context already has a communicator (wb_comm_destroy first)");
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NCCL_CK(api, api->CommInitRank(&comm, world, id, rank));
+  c->comm = comm;
+  c->comm_rank = rank;
+  c->comm_world = world;
+  CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->comm_ev, cudaEventDisableTiming));
+  return 0;
+}
+
+int wb_scatter_frames(wb_ctx* c, int root, const uint8_t* const* send_per_rank, uint8_t* recv, size_t bytes_per_rank,
+                      uint64_t cuda_stream) {
+  REQUIRE(c, "NULL ctx");
+  REQUIRE(c->comm != nullptr, "wb_comm_init has not been called on this context");
+  REQUIRE(root >= 0 && root < c->comm_world, "root out of range");
+  REQUIRE(recv != nullptr && bytes_per_rank > 0, "NULL receive buffer / empty slab");
+  const bool is_root = c->comm_rank == root;
+  REQUIRE(!is_root || send_per_rank != nullptr, "the root rank must pass send_per_rank");
+  if (is_root)
+    for (int r = 0; r < c->comm_world; ++r) REQUIRE(send_per_rank[r] != nullptr, "NULL slab pointer");
+  NcclApi* api = nccl_api();
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  std::lock_guard<std::mutex> lock(c->mu);
+  CK(cudaSetDevice(c->device));
+  const bool own = cuda_stream == 0;
+  cudaStream_t st = own ? c->comm_stream : reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (is_root) {
+    NCCL_CK(api, api->GroupStart());
+    for (int r = 0; r < c->comm_world; ++r)
+      if (r != root) NCCL_CK(api, api->Send(send_per_rank[r], bytes_per_rank, ncclUint8, r, comm, st));
+    NCCL_CK(api, api->GroupEnd());
+    if (send_per_rank[root] != recv)
+      CK(cudaMemcpyAsync(recv, send_per_rank[root], bytes_per_rank, cudaMemcpyDeviceToDevice, st));
+  } else {
+    NCCL_CK(api, api->Recv(recv, bytes_per_rank, ncclUint8, root, comm, st));
+  }
+  if (own) {
+    CK(cudaEventRecord(c->comm_ev, st));
+    for (auto& s : c->slots) CK(cudaStreamWaitEvent(s.stream, c->comm_ev, 0));
+  }
+  return 0;
+}
+
+int wb_comm_destroy(wb_ctx* c) {
+  if (!c || !c->comm) return 0;
+  NcclApi* api = nccl_api();
+  cudaSetDevice(c->device);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (api->handle) api->CommDestroy(static_cast<ncclComm_t>(c->comm));
+  c->comm = nullptr;
+  c->comm_rank = -1;
+  c->comm_world = 0;
+  if (c->comm_ev) cudaEventDestroy(c->comm_ev);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  c->comm_ev = nullptr;
+  c->comm_stream = nullptr;
+  return 0;
+}

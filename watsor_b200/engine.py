@@ -141,6 +141,28 @@ class Engine:
         """direction 0: slot streams wait for `cuda_stream`; 1: `cuda_stream` waits for the slots."""
         check(self.lib.wb_stream_fence(self._ctx, int(cuda_stream), direction))
 
+    # --------------------------------------------------------------- frame scatter (NCCL behind the C-ABI)
+    def comm_unique_id(self):
+        """128-byte rendezvous id; the root rank makes it and ships it to the others over any host channel."""
+        buf = (ctypes.c_uint8 * 128)()
+        check(self.lib.wb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        """Collective over the `world` engines (one per process / GPU)."""
+        assert len(unique_id) == 128
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self.lib.wb_comm_init(self._ctx, rank, world, buf))
+
+    def scatter_frames(self, root, send_ptrs, recv_ptr, nbytes, cuda_stream=0):
+        """send_ptrs: on the root, one device pointer per rank (that rank's `nbytes` slab), else None; recv_ptr:
+        this rank's device buffer.  cuda_stream 0: later submits on this engine are ordered after the scatter."""
+        sp = _ptr_array(send_ptrs) if send_ptrs is not None else None
+        check(self.lib.wb_scatter_frames(self._ctx, root, sp, c_void_p(int(recv_ptr)), nbytes, int(cuda_stream)))
+
+    def comm_destroy(self):
+        check(self.lib.wb_comm_destroy(self._ctx))
+
     # --------------------------------------------------------------- stage level
     def preprocess(self, frames):
         n = len(frames)

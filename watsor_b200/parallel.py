@@ -25,6 +25,23 @@ def scatter_frames(recv, per_rank_frames, src=0):
     dist.scatter(recv, per_rank_frames if dist.get_rank() == src else None, src=src)
 
 
+def init_engine_comm(engine, rank=None, world=None, root=0):
+    """Create the engine's own NCCL communicator (`wb_comm_init`, include/watsor_b200.h): the root makes the 128-byte
+    id through the C-ABI and `torch.distributed` -- any backend, it is only the host-side rendezvous channel --
+    carries it to the other ranks.  After this, `engine_scatter_frames` never touches torch."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    box = [engine.comm_unique_id() if rank == root else None]
+    dist.broadcast_object_list(box, src=root)
+    engine.comm_init(rank, world, box[0])
+
+
+def engine_scatter_frames(engine, recv, per_rank_frames, root=0, cuda_stream=0):
+    """`scatter_frames` through the library's own collective (`wb_scatter_frames`): tensors are only pointer carriers."""
+    send = [int(t.data_ptr()) for t in per_rank_frames] if per_rank_frames is not None else None
+    engine.scatter_frames(root, send, int(recv.data_ptr()), recv.numel() * recv.element_size(), cuda_stream)
+
+
 def max_over_ranks(value, device='cpu'):
     """Every multi-GPU time is the max over ranks (the slowest rank defines the step)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
