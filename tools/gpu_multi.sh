@@ -12,3 +12,9 @@ echo "== bench N=$N"
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 200 --warmup 10 --no-cpu-baseline --no-real-weights --no-worker --no-roofline 2> gpurun_out/${T}_bench_${N}.err | tail -1 > gpurun_out/${T}_bench_${N}.json
 cut -c1-250 gpurun_out/${T}_bench_${N}.json; tail -3 gpurun_out/${T}_bench_${N}.err
+if [ "$N" = "2" ]; then
+  echo "== bench N=$N, scatter through torch.distributed for comparison"
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus $N --steps 200 --warmup 10 --no-cpu-baseline --no-real-weights --no-worker --no-roofline --scatter-impl torch 2> gpurun_out/${T}_bench_${N}_torch.err | tail -1 > gpurun_out/${T}_bench_${N}_torch.json
+  cut -c1-250 gpurun_out/${T}_bench_${N}_torch.json
+fi

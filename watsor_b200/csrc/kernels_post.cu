@@ -150,11 +150,13 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* a, int P) {
 }
 
 // grid (classes, frames), 256 threads.  Per (frame, class):
-//  1. candidate keys -> shared memory.  With many candidates (score threshold 1e-8 makes every anchor one)
-//     only the head of the order is ever visited before max_per_class boxes are kept, so the keys are first
-//     split by a score histogram (11 bits of the float) into a "high" segment of >= NMS_HEAD keys and the
-//     rest; the high segment is sorted (bitonic), the rest only if the greedy pass runs out of candidates.
-//     Every key of the high segment is larger than every key of the rest, so the visiting order is unchanged.
+//  1. candidate keys -> shared memory, in CHUNKS of descending score.  With many candidates (score threshold 1e-8
+//     makes every anchor one) only the head of the order is ever visited before max_per_class boxes are kept or the
+//     early exit fires (most classes stop after two rounds), so the keys are never sorted as a whole: a score
+//     histogram (sign, exponent and 5 mantissa bits of the float: 32 bins per octave) is built once, and each chunk
+//     is "the highest remaining bins that hold >= want keys" (96 for the first chunk, 384 after), gathered from the
+//     L2-resident key list and sorted (bitonic).  A chunk is a whole number of bins and every key of a higher bin is
+//     larger than every key of a lower one, so the visiting order is exactly the descending key order.
 //  2. greedy suppression with exact sequential semantics, 32 candidates per round:
 //     phase 1 (all 8 warps): candidate i vs every box kept in EARLIER rounds (warp w takes candidates
 //     4w..4w+3, lanes stride over the kept list, a ballot decides);
@@ -167,24 +169,29 @@ constexpr int KEPT_BINS = 1024;
 __device__ __forceinline__ int score_bin(unsigned score_bits) {
   return min(KEPT_BINS - 1, max(0, (int)(__uint_as_float(score_bits) * (float)KEPT_BINS)));
 }
-constexpr int NMS_HEAD = 384;
+constexpr int NMS_CHUNK0 = 96;   // keys wanted in the first chunk (three rounds of 32)
+constexpr int NMS_CHUNK = 384;   // ... in every later chunk
 constexpr int NMS_PREFILTER_MIN = 640;
+constexpr int NMS_BINS = 1024;
+// bin of a candidate key, monotone non-decreasing in the key: sign + exponent + 5 mantissa bits of the score, counted
+// from 2^-27 (scores are in (0, 1]: exponents 100..127; anything smaller lands in bin 0)
+__device__ __forceinline__ int nms_bin(unsigned long long key) {
+  return min(NMS_BINS - 1, max(0, (int)(key >> 50) - (100 << 5)));
+}
 
 __global__ void __launch_bounds__(256)
     k_nms(PostParams pp, const float4* __restrict__ dec, const int* __restrict__ cand_count,
           const unsigned long long* __restrict__ cand, int sort_cap, int* __restrict__ sel_count,
           unsigned long long* __restrict__ sel_key, int* __restrict__ sel_idx, int* __restrict__ kept_hist) {
-  extern __shared__ unsigned long long s_dyn[];  // [2][sort_cap]: high segment, low segment
-  unsigned long long* s_a = s_dyn;
-  unsigned long long* s_b = s_dyn + sort_cap;
+  extern __shared__ unsigned long long s_a[];  // [sort_cap]: the current chunk, sorted
   __shared__ float4 s_kept[128];  // normalised corners of the kept boxes
   __shared__ float s_karea[128];
   __shared__ float4 s_cbox[32];  // normalised corners of the round's candidates
   __shared__ float s_carea[32];
   __shared__ float4 s_craw[32];  // as decoded (for the clipped-area test)
   __shared__ unsigned s_alive;   // bit i: candidate i of the round survived phase 1
-  __shared__ int s_nkept_sh, s_na, s_nb, s_cut;
-  __shared__ int s_hist[1024];
+  __shared__ int s_nkept_sh, s_na, s_cut;
+  __shared__ int s_hist[NMS_BINS];
   __shared__ int s_above[8];
   int* fhist = kept_hist + (size_t)blockIdx.y * KEPT_BINS;  // this frame's histogram of kept, selectable scores
   const int c = blockIdx.x, f = blockIdx.y, C = pp.num_classes, N = pp.num_anchors;
@@ -199,97 +206,93 @@ __global__ void __launch_bounds__(256)
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long* ck = cand + ((size_t)f * C + c) * N;
-  int n_a = n, n_b = 0;
-  if (n <= NMS_PREFILTER_MIN) {
-    int P = 32;
-    while (P < n) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_a[i] = i < n ? ck[i] : 0ull;
-    __syncthreads();
-    bitonic_desc(s_a, P);
-  } else {
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_hist[i] = 0;
-    if (threadIdx.x == 0) s_na = s_nb = 0;
+  const bool chunked = n > NMS_PREFILTER_MIN;
+  if (chunked) {
+    for (int i = threadIdx.x; i < NMS_BINS; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-      // scores of one class crowd into a handful of bins (most are ~0.01): aggregate equal bins inside the warp
-      // (__match_any_sync) so that one lane per distinct bin issues the shared-memory atomic
+      // scores of one class crowd into few bins: aggregate equal bins inside the warp (__match_any_sync) so that one
+      // lane per distinct bin issues the shared-memory atomic
       const int i = i0 + threadIdx.x;
-      const int bin = i < n ? min((int)(ck[i] >> 52), 1023) : -1;  // sign + exponent + 3 mantissa bits of the score
+      const int bin = i < n ? nms_bin(ck[i]) : -1;
       const unsigned peers = __match_any_sync(0xffffffffu, bin);
       if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
     }
-    __syncthreads();
-    if (warp == 0) {  // highest bins first until NMS_HEAD keys are covered
-      int acc = 0, cut = 0;
-      for (int top = 1023; top >= 0 && acc < NMS_HEAD; top -= 32) {
-        const int b = top - lane;
-        const int v = b >= 0 ? s_hist[b] : 0;
-        int incl = v;  // inclusive prefix over lanes (lane 0 = highest bin)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const unsigned reach = __ballot_sync(0xffffffffu, acc + incl >= NMS_HEAD);
-        if (reach) {
-          const int l = __ffs(reach) - 1;
-          cut = top - l;
-          acc += __shfl_sync(0xffffffffu, incl, l);
-          break;
-        }
-        acc += __shfl_sync(0xffffffffu, incl, 31);
-        cut = max(top - 31, 0);
-      }
-      if (lane == 0) s_cut = cut;
-    }
-    __syncthreads();
-    const int cut = s_cut;
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {  // second pass over the L2-resident keys
-      const int i = i0 + threadIdx.x;
-      const unsigned long long k = i < n ? ck[i] : 0ull;
-      const bool hi = i < n && min((int)(k >> 52), 1023) >= cut, lo = i < n && !hi;
-      // warp-aggregated append: one shared-memory atomic per warp and segment instead of one per key
-      const unsigned mh = __ballot_sync(0xffffffffu, hi), ml = __ballot_sync(0xffffffffu, lo);
-      int bh = 0, bl = 0;
-      if (lane == 0) {
-        if (mh) bh = atomicAdd(&s_na, __popc(mh));
-        if (ml) bl = atomicAdd(&s_nb, __popc(ml));
-      }
-      bh = __shfl_sync(0xffffffffu, bh, 0);
-      bl = __shfl_sync(0xffffffffu, bl, 0);
-      const unsigned lt = (1u << lane) - 1u;
-      if (hi) s_a[bh + __popc(mh & lt)] = k;
-      if (lo) s_b[bl + __popc(ml & lt)] = k;
-    }
-    __syncthreads();
-    n_a = s_na;
-    n_b = s_nb;
-    int P = 32;
-    while (P < n_a) P <<= 1;
-    for (int i = n_a + threadIdx.x; i < P; i += blockDim.x) s_a[i] = 0ull;
-    __syncthreads();
-    bitonic_desc(s_a, P);
   }
-
   const float4* fdec = dec + (size_t)f * N;
   if (threadIdx.x == 0) s_nkept_sh = 0;
   __syncthreads();
+
   bool stop = false;
-  for (int seg = 0; seg < 2 && !stop; ++seg) {
-    const unsigned long long* sorted = seg == 0 ? s_a : s_b;
-    const int count = seg == 0 ? n_a : n_b;
-    if (seg == 1) {
-      if (count == 0 || s_nkept_sh >= max_out) break;  // uniform: s_nkept_sh was published before a barrier
+  int hi_bin = NMS_BINS;  // bins >= hi_bin have been visited
+  for (int chunk = 0; !stop; ++chunk) {
+    int count;
+    if (!chunked) {
+      if (chunk > 0) break;
+      int P = 32;
+      while (P < n) P <<= 1;
+      for (int i = threadIdx.x; i < P; i += blockDim.x) s_a[i] = i < n ? ck[i] : 0ull;
+      __syncthreads();
+      bitonic_desc(s_a, P);
+      count = n;
+    } else {
+      if (hi_bin <= 0 || s_nkept_sh >= max_out) break;  // uniform: both were published before a barrier
+      const int want = chunk == 0 ? NMS_CHUNK0 : NMS_CHUNK;
+      if (warp == 0) {  // highest remaining bins first until `want` keys are covered (or nothing is left: cut = 0)
+        int acc = 0, cut = 0;
+        for (int top = hi_bin - 1; top >= 0 && acc < want; top -= 32) {
+          const int b = top - lane;
+          const int v = b >= 0 ? s_hist[b] : 0;
+          int incl = v;  // inclusive prefix over lanes (lane 0 = highest bin)
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const unsigned reach = __ballot_sync(0xffffffffu, acc + incl >= want);
+          if (reach) {
+            const int l = __ffs(reach) - 1;
+            cut = top - l;
+            acc += __shfl_sync(0xffffffffu, incl, l);
+            break;
+          }
+          acc += __shfl_sync(0xffffffffu, incl, 31);
+          cut = max(top - 31, 0);
+        }
+        if (lane == 0) {
+          s_cut = cut;
+          s_na = 0;
+        }
+      }
+      __syncthreads();
+      const int cut = s_cut;
+      for (int i0 = 0; i0 < n; i0 += blockDim.x) {  // pass over the L2-resident keys: bins [cut, hi_bin)
+        const int i = i0 + threadIdx.x;
+        const unsigned long long k = i < n ? ck[i] : 0ull;
+        const int bin = nms_bin(k);
+        const bool in = i < n && bin >= cut && bin < hi_bin;
+        // warp-aggregated append: one shared-memory atomic per warp instead of one per key
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        int base_pos = 0;
+        if (lane == 0 && m) base_pos = atomicAdd(&s_na, __popc(m));
+        base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+        if (in) s_a[base_pos + __popc(m & ((1u << lane) - 1u))] = k;
+      }
+      __syncthreads();
+      count = s_na;
+      hi_bin = cut;
+      if (count == 0) continue;  // uniform; an empty range can only be the last one (cut == 0)
       int P = 32;
       while (P < count) P <<= 1;
-      for (int i = count + threadIdx.x; i < P; i += blockDim.x) s_b[i] = 0ull;
+      for (int i = count + threadIdx.x; i < P; i += blockDim.x) s_a[i] = 0ull;
       __syncthreads();
-      bitonic_desc(s_b, P);
+      bitonic_desc(s_a, P);
     }
+    const unsigned long long* sorted = s_a;
     for (int base = 0; base < count; base += 32) {
       const int nkept = s_nkept_sh;
       if (nkept >= max_out) break;
-      if (base > 0 || seg > 0) {
+      if (base > 0 || chunk > 0) {
         // Early exit (exact): the frame-wide histogram counts boxes that some class has already KEPT with a positive
         // clipped area -- final facts.  If max_total of them sit in score bins strictly above this class's best
         // remaining candidate, neither it nor anything after it can reach the frame's top max_total, and whatever
@@ -608,7 +611,7 @@ void launch_post(const LaunchCtx& lc, int n, const PostParams& pp, const float* 
     cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done.set();
   }
-  k_nms<<<dim3(C, n), 256, 2 * sizeof(unsigned long long) * sort_cap, lc.stream>>>(
+  k_nms<<<dim3(C, n), 256, sizeof(unsigned long long) * sort_cap, lc.stream>>>(
       pp, reinterpret_cast<const float4*>(dec_boxes), cand_count, cand, sort_cap, sel_count, sel_key, sel_idx, kept_hist);
   ++*lc.launch_counter;
   {

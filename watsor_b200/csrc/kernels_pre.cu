@@ -141,7 +141,10 @@ __device__ __forceinline__ void resized_pixel_staged(const FrameDesc& fd, const 
 // bytes per staged row for frames up to `max_src_w` wide resized to `in_w`, tile of `tile_w` resized columns; 0 = do
 // not stage (unknown width, or the rows would not fit)
 static int stage_pitch_for(int max_src_w, int in_w, int tile_w, int rows) {
-  if (max_src_w <= 0 || getenv("WB_NO_STAGE")) return 0;
+  // opt-in (WB_STAGE=1): measured slower than the direct path on B200 (profiles/r02_stem.md) -- the byte loads hit L1
+  // and the kernel is issue bound, not latency bound
+  const char* on = getenv("WB_STAGE");
+  if (max_src_w <= 0 || on == nullptr || on[0] != '1' || getenv("WB_NO_STAGE")) return 0;
   const double scale = (double)max_src_w / in_w;
   int px = (int)(tile_w * (scale > 1.0 ? scale : 1.0)) + 4;
   if (px > max_src_w) px = max_src_w;
