@@ -154,6 +154,46 @@ int wb_scatter_frames(wb_ctx* ctx, int root, const uint8_t* const* send_per_rank
                       size_t bytes_per_rank, uint64_t cuda_stream);
 int wb_comm_destroy(wb_ctx* ctx);
 
+/* ---- visual effects of the output stage, SURVEY.md section 8 (f)4 -------------------------------------------------
+ * One CUDA pass per batch of frames replaces the effect chain of watsor/main.py:302-312:
+ *   CopyImageEffect (output/copy.py:14-18) or BlendEffect (output/blend.py:8-32), then DrawEffect (output/draw.py:9-88)
+ *   or DrawEffectWithContours (draw.py:91-103).  Output bytes equal the reference's (numpy + OpenCV on the CPU).
+ * The label text is cv2.putText's: the host builds per-glyph tables with the installed OpenCV
+ * (watsor_b200/output/font.py) and the kernel applies them; zone outlines are cv2.drawContours rasters made once per
+ * camera.  An effects context is independent of a detector context (the reference runs effects in their own process
+ * per camera, output/video.py:10-35). */
+typedef struct wb_fx wb_fx;
+typedef struct wb_fx_font {
+  int32_t n_glyphs;
+  int32_t rows, cols, y0;         /* glyph window: cols x rows pixels, first row at org.y + y0, first column at the pen */
+  int32_t text_height, baseline;  /* cv2.getTextSize(...) of FONT_HERSHEY_DUPLEX, scale 0.5, thickness 1   draw.py:56-59 */
+  int32_t margin;                 /* int(round(ceil(0.1 * text_height)))                                    draw.py:62 */
+  const int32_t* advance;         /* [n_glyphs] pen advance in half pixels */
+  const uint8_t* lut;             /* [n_glyphs][2 phases][cols + 1 clip distances][rows][cols][256] */
+} wb_fx_font;
+typedef struct wb_fx_label {      /* drawing attributes of one label index (config/coco.py:110-121) */
+  uint8_t box_color[3];
+  uint8_t n_prefix;               /* "<label>: " as glyph indices */
+  uint8_t prefix[60];
+} wb_fx_label;
+#define WB_FX_BLEND 1u     /* BlendEffect for cameras that have an alpha channel (else the image is copied) */
+#define WB_FX_DRAW 2u      /* DrawEffect */
+#define WB_FX_CONTOURS 4u  /* ... WithContours */
+#define WB_FX_ON_DEVICE 8u /* images_in / images_out are device pointers */
+/* labels[0] is also the style of unknown label indices (coco.py:124-131); digit_glyphs = glyph indices of '0'..'9','%';
+ * alpha = opacity of the label box (coco.py:119) */
+int wb_fx_create(int device, const wb_fx_font* font, int n_labels, const wb_fx_label* labels,
+                 const uint8_t* digit_glyphs, double alpha, wb_fx** out);
+/* alpha: [height][width] alpha channel of the mask image (filter/mask.py:71-81) or NULL; contour_bits: [height][width]
+ * uint32, bit z-1 set where cv2.drawContours(contours, z-1, thickness=1) paints, or NULL */
+int wb_fx_set_camera(wb_fx* fx, int cam_id, int width, int height, const uint8_t* alpha, const uint32_t* contour_bits);
+/* rows[i]: the 100 Detection rows of frame i (host memory: header.detections).  images: RGB24, host pointers unless
+ * WB_FX_ON_DEVICE.  gpu_ms: kernels only. */
+int wb_fx_render(wb_fx* fx, int n, const uint8_t* const* images_in, uint8_t* const* images_out, const int32_t* cam_ids,
+                 const wb_detection* const* rows, uint32_t flags, float* gpu_ms);
+int wb_fx_destroy(wb_fx* fx);
+const char* wb_fx_last_error(void);
+
 /* ---- stage-level entry points (parity tests call the same kernels stage by stage) -------------- */
 /* graph nodes Cast + Preprocessor/... : out = float32 [n][in_h][in_w][3] on the host */
 int wb_preprocess(wb_ctx* ctx, int n, const uint8_t* const* frames, const int32_t* widths,
