@@ -67,6 +67,7 @@ def parse_args():
                    help="cabi: the library's own communicator (wb_comm_init / wb_scatter_frames); torch: "
                         'torch.distributed.scatter')
     p.add_argument('--no-worker', action='store_true', help='skip the e2e_worker record')
+    p.add_argument('--no-effects', action='store_true', help='skip the visual-effects record')
     p.add_argument('--min-seconds', type=float, default=1.0,
                    help='the *_long / e2e measurements run at least this long')
     return p.parse_args()
@@ -540,6 +541,10 @@ def main():
     if rank == 0 and not args.no_worker:
         worker = measure_worker(args, local_rank, m)
 
+    effects = None
+    if rank == 0 and world == 1 and not args.no_effects:
+        effects = measure_effects(args, local_rank, torch)
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         run, cores, host_cores = oracle_step_fn(arm.model, args)
@@ -600,6 +605,7 @@ def main():
             'e2e': m['e2e'],
             'e2e_k': m['e2e_k'],
             'e2e_worker': worker,
+            'effects': effects,
             'scatter': scatter,
             'gpu_launches': m['launches_per_step'] * args.steps,
             'gpu_launches_per_step': m['launches_per_step'],
@@ -610,6 +616,68 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_effects(args, local_rank, torch):
+    """Auxiliary record (not part of the headline): the output stage's effect chain of main.py:302-312
+    -- BlendEffect + DrawEffectWithContours -- for the same 8 masked cameras as one `wb_fx_render` per tick, with 8
+    labelled detections per frame.  `value`: frames resident on the device, kernels only (CUDA events inside the
+    library); `e2e`: host frames in, host frames out, wall clock.  HBM roofline: 3 B read + 3 B written per pixel
+    plus the alpha channel (1 B) and the zone-outline raster (4 B)."""
+    try:
+        from tests.fx_cases import random_rows
+        from watsor_b200.filter.mask import get_alpha_channel
+        from watsor_b200.output.effects import (WB_FX_BLEND, WB_FX_CONTOURS, WB_FX_DRAW, WB_FX_ON_DEVICE,
+                                                EffectsEngine, contour_bits)
+        C = args.cameras
+        rng = np.random.default_rng(3)
+        t0 = time.perf_counter()
+        eng = EffectsEngine(local_rank)
+        init_s = time.perf_counter() - t0
+        cams, rows, imgs = [], [], []
+        for c in range(C):
+            cfg = camera_config(c, args.model)
+            alpha = cont = None
+            if 'mask' in cfg:
+                alpha, _ = get_alpha_channel(cfg['mask'], W, H)
+                cont = contour_bits(alpha)
+            cams.append(eng.add_camera(W, H, alpha, cont))
+            rows.append(random_rows(rng, W, H, 8, n_zones=1))
+            imgs.append(make_frames(args.model, c, 1)[0])
+        flags = WB_FX_BLEND | WB_FX_DRAW | WB_FX_CONTOURS
+        d_in = [torch.from_numpy(np.ascontiguousarray(i)).cuda() for i in imgs]
+        d_out = [torch.empty_like(t) for t in d_in]
+        torch.cuda.synchronize()
+        pin, pout = [t.data_ptr() for t in d_in], [t.data_ptr() for t in d_out]
+        for _ in range(5):
+            eng.render(pin, pout, cams, rows, flags | WB_FX_ON_DEVICE)
+        ms = [eng.render(pin, pout, cams, rows, flags | WB_FX_ON_DEVICE) for _ in range(200)]
+        med = float(np.median(ms))
+        outs = [np.empty_like(i) for i in imgs]
+        for _ in range(3):
+            eng.render(imgs, outs, cams, rows, flags)
+        t0 = time.perf_counter()
+        reps = 30
+        for _ in range(reps):
+            eng.render(imgs, outs, cams, rows, flags)
+        wall = (time.perf_counter() - t0) / reps
+        eng.close()
+        alg = C * W * H * 11
+        peak = 6650.0
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.isfile(pk):
+            peak = json.load(open(pk)).get('hbm_gbs', peak)
+        rec = {'value': C / (med / 1e3), 'unit': 'frames/s', 'ms_per_tick': med, 'frames_per_tick': C,
+               'drawn_detections_per_frame': 8, 'chain': 'BlendEffect + DrawEffectWithContours (CopyImageEffect + '
+               'DrawEffect on cameras without a mask), one wb_fx_render per tick',
+               'algorithmic_bytes_per_tick': alg, 'achieved_gbps': alg / (med / 1e3) / 1e9,
+               'e2e': {'value': C / wall, 'unit': 'frames/s', 'h2d_bytes_per_tick': C * W * H * 3 + C * 7200,
+                       'd2h_bytes_per_tick': C * W * H * 3}, 'engine_init_s': init_s}
+        if peak:
+            rec['hbm_frac'] = rec['achieved_gbps'] / peak
+        return rec
+    except Exception as e:          # auxiliary: never takes the headline down
+        return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
 def measure_worker(args, local_rank, headline):

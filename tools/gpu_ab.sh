@@ -2,7 +2,7 @@
 # A/B of opt-in switches: short bench runs (device value + e2e), plus the tensor-core tests under the switch
 mkdir -p gpurun_out
 T=${1:-r2ab}
-B="python bench.py --steps 400 --warmup 10 --no-cpu-baseline --no-real-weights --no-worker --no-roofline"
+B="python bench.py --steps 400 --warmup 10 --no-cpu-baseline --no-real-weights --no-worker --no-effects --no-roofline"
 for cfg in "default" "WB_GEMM_2CTA=1" "WB_TMEM_A=1" "WB_GEMM_2CTA=1 WB_WIDE_N=1"; do
   name=$(echo "$cfg" | tr ' =' '__')
   if [ "$cfg" = "default" ]; then env timeout 300 $B 2>/dev/null | tail -1 > gpurun_out/${T}_${name}.json

@@ -17,30 +17,30 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | 
 echo "== bench (default)"
 timeout 900 python bench.py 2> gpurun_out/r02_bench.err | tail -1 > gpurun_out/r02_bench_line.json; cut -c1-300 gpurun_out/r02_bench_line.json
 echo "== bench --steps 20 --warmup 5 (the driver's length)"
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-worker --no-real-weights 2>/dev/null | tail -1 > gpurun_out/r02_bench_k20.json; cut -c1-200 gpurun_out/r02_bench_k20.json
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-worker --no-effects --no-real-weights 2>/dev/null | tail -1 > gpurun_out/r02_bench_k20.json; cut -c1-200 gpurun_out/r02_bench_k20.json
 echo "== bench --impl reference"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_reference_line.json; cut -c1-300 gpurun_out/r02_bench_reference_line.json
 echo "== bench --model inception --cameras 2 (configs[4] per GPU)"
 timeout 600 python bench.py --model inception --cameras 2 --steps 200 --warmup 10 --no-worker 2>/dev/null | tail -1 > gpurun_out/r02_bench_inception.json; cut -c1-300 gpurun_out/r02_bench_inception.json
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
-    --log-file gpurun_out/launches_r02.csv python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_list.log 2>&1
+    --log-file gpurun_out/launches_r02.csv python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > gpurun_out/r02_ncu_list.log 2>&1
 tail -1 gpurun_out/r02_ncu_list.log | cut -c1-120
 echo "== ncu --set full (one step of tcgen05 launches; the report stays on the box, its raw page comes back as CSV)"
 timeout 900 ncu --set full --clock-control none -k regex:'k_gemm_tc|k_dwpw|k_irb' -s 300 -c 48 \
-    -o /tmp/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
+    -o /tmp/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
 tail -1 gpurun_out/r02_ncu_full.log | cut -c1-120
 ncu -i /tmp/prof_r02.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
 echo "== stem / resize kernels: time + DRAM bytes (640x480 bench, 1920x1080 inception bench, stand-alone kernel)"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640.csv \
-    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > /dev/null 2>&1
+    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_1080.csv \
-    python bench.py --model inception --cameras 2 --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-worker --min-seconds 0 > /dev/null 2>&1
+    python bench.py --model inception --cameras 2 --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess.csv \
     python tools/pre_probe.py > gpurun_out/r02_pre_probe.log 2>&1
 WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640_nostage.csv \
-    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --min-seconds 0 > /dev/null 2>&1
+    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
 WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess_nostage.csv \
     python tools/pre_probe.py > /dev/null 2>&1
 grep -h "gpu__time" gpurun_out/r02_stem_640.csv gpurun_out/r02_stem_640_nostage.csv gpurun_out/r02_stem_1080.csv gpurun_out/r02_preprocess.csv gpurun_out/r02_preprocess_nostage.csv | cut -d, -f5,13- | head -30

@@ -89,6 +89,12 @@ def load():
         'wb_debug_pyset_order': (c_int, [P(c_int32), c_int, P(c_int32), P(c_int)]),
         'wb_debug_unused_order': (c_int, [c_int, c_void_p, P(c_int32), P(c_int)]),
         'wb_debug_argsort': (c_int, [c_void_p, c_int, P(c_int32)]),
+        'wb_fx_create': (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_double, P(c_void_p)]),
+        'wb_fx_set_camera': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+        'wb_fx_render': (c_int, [c_void_p, c_int, P(c_void_p), P(c_void_p), P(c_int32), P(c_void_p), c_uint32,
+                                 P(c_float)]),
+        'wb_fx_destroy': (c_int, [c_void_p]),
+        'wb_fx_last_error': (c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
@@ -106,7 +112,8 @@ EXPORTS = ['wb_abi_version', 'wb_last_error', 'wb_device_count', 'wb_create', 'w
            'wb_scatter_frames', 'wb_comm_destroy', 'wb_preprocess', 'wb_backbone',
            'wb_postprocess', 'wb_filter_rows', 'wb_anchors', 'wb_last_launch_count', 'wb_profile_layers',
            'wb_tracker_create', 'wb_tracker_destroy', 'wb_tracker_update', 'wb_sieve_rows', 'wb_debug_pyset_order',
-           'wb_debug_unused_order', 'wb_debug_argsort']
+           'wb_debug_unused_order', 'wb_debug_argsort', 'wb_fx_create', 'wb_fx_set_camera', 'wb_fx_render',
+           'wb_fx_destroy', 'wb_fx_last_error']
 
 
 def check(rc):

@@ -16,12 +16,24 @@ toothbrush"""
 COCO_CLASSES = ['unlabeled'] + [w.replace('_', ' ') for w in _THINGS.split()]
 assert len(COCO_CLASSES) == 91
 
-CocoClass = namedtuple('CocoClass', ['index', 'label'])
+CocoClass = namedtuple('CocoClass', ['index', 'label', 'box_color', 'font_color', 'box_thickness', 'font_thickness',
+                                     'font_scale', 'alpha'])
+
+# Drawing attributes of the output stage (watsor/config/coco.py:107-121): one random RGB colour per label from a fixed
+# seed, white text, 1-pixel box and strokes, font scale 0.5, label box opacity 0.55.
+_BOX_COLORS = None
+
+
+def _box_colors():
+    global _BOX_COLORS
+    if _BOX_COLORS is None:
+        import numpy as np
+        _BOX_COLORS = np.random.RandomState(255).uniform(0, 255, size=(len(COCO_CLASSES), 3)).astype(np.uint8)
+    return _BOX_COLORS
 
 
 def get_coco_class(idx):
-    """Label record for an index; unknown indices map to 'unlabeled' (coco.py:124-131).  The reference's record
-    also carries drawing attributes (box / font colours) for its output stage, which is out of scope here."""
-    if 0 <= idx < len(COCO_CLASSES):
-        return CocoClass(idx, COCO_CLASSES[idx])
-    return CocoClass(0, COCO_CLASSES[0])
+    """Record for a label index; unknown indices map to 'unlabeled' (coco.py:124-131)."""
+    if not 0 <= idx < len(COCO_CLASSES):
+        idx = 0
+    return CocoClass(idx, COCO_CLASSES[idx], tuple(int(v) for v in _box_colors()[idx]), (255, 255, 255), 1, 1, 0.5, 0.55)

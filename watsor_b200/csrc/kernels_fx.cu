@@ -465,6 +465,11 @@ int wb_fx_render(wb_fx* fx, int n, const uint8_t* const* images_in, uint8_t* con
     auto it = fx->cams.find(cam_ids[i]);
     FXREQ(it != fx->cams.end(), "cam_id " + std::to_string(cam_ids[i]) + " has not been configured with wb_fx_set_camera");
     FXREQ(images_in[i] && images_out[i] && rows[i], "NULL frame / rows pointer");
+    // labels are placed inside the frame only if it is high enough for one above/below/inside a box (draw.py:68-73);
+    // lower frames would need OpenCV's re-capping of strokes cut by the bottom border, which the tables do not hold
+    const int min_h = 2 * (fx->font.text_height + 2 * fx->font.margin + fx->font.baseline) + 1;
+    FXREQ(!(flags & WB_FX_DRAW) || it->second.h >= min_h,
+          "the draw effect needs frames of at least " + std::to_string(min_h) + " rows");
     total += ((size_t)it->second.w * it->second.h * 3 + 255) / 256 * 256;
     max_w = std::max(max_w, it->second.w);
     max_h = std::max(max_h, it->second.h);
