@@ -653,7 +653,10 @@ def measure_effects(args, local_rank, torch):
             eng.render(pin, pout, cams, rows, flags | WB_FX_ON_DEVICE)
         ms = [eng.render(pin, pout, cams, rows, flags | WB_FX_ON_DEVICE) for _ in range(200)]
         med = float(np.median(ms))
-        outs = [np.empty_like(i) for i in imgs]
+        # host frames in pinned memory, like the shared frame buffers the worker registers (wb_register_host)
+        pinned_in = [torch.from_numpy(np.ascontiguousarray(i)).pin_memory() for i in imgs]
+        pinned_out = [torch.empty_like(t).pin_memory() for t in pinned_in]
+        imgs, outs = [t.numpy() for t in pinned_in], [t.numpy() for t in pinned_out]
         for _ in range(3):
             eng.render(imgs, outs, cams, rows, flags)
         t0 = time.perf_counter()

@@ -189,8 +189,9 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// grid (ceil(W / 128), ceil(H / 8), frames), 256 threads; thread = 4 consecutive pixels of one row.
-constexpr int FX_TW = 128, FX_TH = 8;
+// grid (ceil(W / 128), ceil(H / 32), frames), 256 threads; thread = 4 consecutive pixels in each of 4 rows (the list of
+// detections that touch the tile is built once per block).
+constexpr int FX_TW = 128, FX_TH = 32, FX_ROWS = FX_TH / 8;
 
 __global__ void __launch_bounds__(256)
     k_fx_render(const FxFrameDesc* __restrict__ frames, const FxFrame* __restrict__ prep, FxFont font,
@@ -230,9 +231,11 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     n_here = s_n;
   }
-  const int y = ty0 + t / (FX_TW / 4);
   const int xb = tx0 + (t % (FX_TW / 4)) * 4;
-  if (y >= H || xb >= W) return;
+  if (xb >= W) return;
+  for (int j = 0; j < FX_ROWS; ++j) {
+  const int y = ty0 + t / (FX_TW / 4) + 8 * j;
+  if (y >= H) break;
   const size_t row = (size_t)y * W;
   const int npx = min(4, W - xb);
   uint8_t v[4][3];
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(256)
     for (int p = 0; p < npx; ++p)
       for (int c = 0; c < 3; ++c) dst[p * 3 + c] = v[p][c];
   }
+  }  // rows of this thread
 }
 
 }  // namespace

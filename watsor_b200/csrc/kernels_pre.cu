@@ -48,6 +48,29 @@ __device__ __forceinline__ void resized_pixel(const uint8_t* __restrict__ img, i
   }
 }
 
+// resized_pixel() in two halves, so that a thread can have the 12 byte loads of a second pixel in flight while it
+// lerps the first one (same operations in the same order: bit-identical)
+__device__ __forceinline__ void resized_pixel_load(const uint8_t* __restrict__ img, int w, const AxisTap& ty,
+                                                   const AxisTap& tx, uint32_t (&raw)[12]) {
+  const uint8_t* r0 = img + (size_t)ty.lo * w * 3;
+  const uint8_t* r1 = img + (size_t)ty.hi * w * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    raw[c * 4 + 0] = __ldg(r0 + tx.lo * 3 + c);
+    raw[c * 4 + 1] = __ldg(r0 + tx.hi * 3 + c);
+    raw[c * 4 + 2] = __ldg(r1 + tx.lo * 3 + c);
+    raw[c * 4 + 3] = __ldg(r1 + tx.hi * 3 + c);
+  }
+}
+__device__ __forceinline__ void resized_pixel_lerp(const uint32_t (&raw)[12], float lx, float ly, float mul, float sub,
+                                                   float* out3) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = lerp_px((float)raw[c * 4 + 0], (float)raw[c * 4 + 1], (float)raw[c * 4 + 2], (float)raw[c * 4 + 3], lx, ly);
+    out3[c] = __fsub_rn(__fmul_rn(mul, v), sub);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Source staging.  `resized_pixel` above issues 12 dependent single-byte global loads per resized pixel; a CTA that
 // builds a tile of resized pixels instead copies the source rows the tile samples into shared memory with aligned
@@ -328,7 +351,15 @@ __global__ void __launch_bounds__(256)
   const int f = blockIdx.z;
   const int oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
   const int tid = threadIdx.x;
-  for (int i = tid; i < K * K * 3 * OC; i += 256) s_w[i] = w[(i / OC) * L.n_pad + (i % OC)];
+  // the 864 weights go through registers: the loads are issued here and waited for after the tile has been built
+  // (13 % of the kernel's stall samples sat on this copy when it stored right away)
+  constexpr int WREGS = (K * K * 3 * OC + 255) / 256;
+  float wreg[WREGS];
+#pragma unroll
+  for (int j = 0; j < WREGS; ++j) {
+    const int i = tid + j * 256;
+    wreg[j] = i < K * K * 3 * OC ? __ldg(w + (i / OC) * L.n_pad + (i % OC)) : 0.f;
+  }
   const int ry0 = oy0 * S - (int)L.pad_t, rx0 = ox0 * S - (int)L.pad_l;
   FrameDesc fd;
   float sy = 1.f, sx = 1.f;
@@ -345,6 +376,37 @@ __global__ void __launch_bounds__(256)
       __syncthreads();
     }
   }
+  if (pre == nullptr && !sp.on) {
+    // two pixels per round: the byte loads of both are in flight before either is interpolated
+    for (int i0 = tid; i0 < tile_h * tile_w; i0 += 512) {
+      uint32_t raw[2][12];
+      AxisTap tys[2], txs[2];
+      bool inside[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * 256;
+        const int ly = i / tile_w, lx = i - ly * tile_w;
+        const int ry = ry0 + ly, rx = rx0 + lx;
+        inside[u] = i < tile_h * tile_w && ry >= 0 && ry < in_h && rx >= 0 && rx < in_w;
+        if (inside[u]) {
+          tys[u] = axis_tap(ry, fd.h, sy);
+          txs[u] = axis_tap(rx, fd.w, sx);
+          resized_pixel_load(fd.ptr, fd.w, tys[u], txs[u], raw[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * 256;
+        if (i < tile_h * tile_w) {
+          float v[3] = {0.f, 0.f, 0.f};
+          if (inside[u]) resized_pixel_lerp(raw[u], txs[u].lerp, tys[u].lerp, mul, sub, v);
+          s_in[i * 3 + 0] = v[0];
+          s_in[i * 3 + 1] = v[1];
+          s_in[i * 3 + 2] = v[2];
+        }
+      }
+    }
+  } else
   for (int i = tid; i < tile_h * tile_w; i += 256) {
     int ly = i / tile_w, lx = i - ly * tile_w;
     int ry = ry0 + ly, rx = rx0 + lx;
@@ -366,6 +428,11 @@ __global__ void __launch_bounds__(256)
     s_in[i * 3 + 0] = v[0];
     s_in[i * 3 + 1] = v[1];
     s_in[i * 3 + 2] = v[2];
+  }
+#pragma unroll
+  for (int j = 0; j < WREGS; ++j) {
+    const int i = tid + j * 256;
+    if (i < K * K * 3 * OC) s_w[i] = wreg[j];
   }
   __syncthreads();
 
