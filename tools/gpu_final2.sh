@@ -31,18 +31,14 @@ timeout 900 ncu --set full --clock-control none -k regex:'k_gemm_tc|k_dwpw|k_irb
     -o /tmp/prof_r02 -f python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > gpurun_out/r02_ncu_full.log 2>&1
 tail -1 gpurun_out/r02_ncu_full.log | cut -c1-120
 ncu -i /tmp/prof_r02.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
-echo "== stem / resize kernels: time + DRAM bytes (640x480 bench, 1920x1080 inception bench, stand-alone kernel)"
+echo "== stem kernel of the final build: time + DRAM bytes (the staging A/B of profiles/r02_stem.md was run earlier)"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640.csv \
+timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640_final.csv \
     python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
-timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_1080.csv \
-    python bench.py --model inception --cameras 2 --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
-timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess.csv \
-    python tools/pre_probe.py > gpurun_out/r02_pre_probe.log 2>&1
-WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_stem' -s 6 -c 4 --csv --log-file gpurun_out/r02_stem_640_nostage.csv \
-    python bench.py --steps 6 --warmup 3 --inflight 1 --no-cpu-baseline --no-roofline --no-real-weights --no-worker --no-effects --min-seconds 0 > /dev/null 2>&1
-WB_NO_STAGE=1 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_preprocess' --csv --log-file gpurun_out/r02_preprocess_nostage.csv \
-    python tools/pre_probe.py > /dev/null 2>&1
-grep -h "gpu__time" gpurun_out/r02_stem_640.csv gpurun_out/r02_stem_640_nostage.csv gpurun_out/r02_stem_1080.csv gpurun_out/r02_preprocess.csv gpurun_out/r02_preprocess_nostage.csv | cut -d, -f5,13- | head -30
+grep -h "gpu__time" gpurun_out/r02_stem_640_final.csv | awk -F'","' '{print $NF}' | head -4
+echo "== effects kernels: time + DRAM bytes"
+timeout 300 ncu --metrics $M --clock-control none -k regex:'k_fx' -c 12 --csv --log-file gpurun_out/r02_fx.csv \
+    python -m pytest tests/test_gpu_effects.py -m gpu -q -k "batch_of_cameras" > /dev/null 2>&1
+grep -h "gpu__time\|dram__" gpurun_out/r02_fx.csv | awk -F'","' '{print $1, $(NF-2), $NF}' | cut -c1-160 | head -12
 ls -la /tmp/prof_r02.ncu-rep gpurun_out/r02_ncu_full_raw.csv gpurun_out/launches_r02.csv
 du -sh gpurun_out
