@@ -135,3 +135,60 @@ def test_errors_are_loud(engine):
     out = np.ones_like(img)
     engine.render([img], [out], [cam], [rows], WB_FX_BLEND)          # no alpha channel: a copy
     assert np.array_equal(out, img)
+
+
+def test_equal_to_the_reference_classes_installed_under_baseline_ref(engine):
+    """The UNMODIFIED reference package (baseline/_ref, installed by __graft_entry__.build(), travels to the GPU box)
+    provides watsor.output.{blend,draw,copy}: run the reference's own effect chain on the CPU and the fused GPU effect
+    on the same frame and rows.  watsor.filter.mask imports shapely (absent): an empty stand-in satisfies the import."""
+    import sys
+    import types
+
+    from tests.conftest import ROOT
+    from watsor_b200.output.effects import FusedEffects
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isfile(os.path.join(ref_root, 'watsor', 'output', 'draw.py')):
+        pytest.skip('baseline/_ref not installed')
+    saved = {k: v for k, v in sys.modules.items() if k == 'shapely' or k.startswith('shapely.') or
+             k == 'watsor' or k.startswith('watsor.')}
+    for k in saved:
+        del sys.modules[k]
+    shapely, geometry = types.ModuleType('shapely'), types.ModuleType('shapely.geometry')
+    geometry.Polygon = object
+    shapely.geometry = geometry
+    sys.modules['shapely'], sys.modules['shapely.geometry'] = shapely, geometry
+    sys.path.insert(0, ref_root)
+    try:
+        from watsor.output.blend import BlendEffect as RefBlend
+        from watsor.output.copy import CopyImageEffect as RefCopy
+        from watsor.output.draw import DrawEffect as RefDraw
+        from watsor.output.draw import DrawEffectWithContours as RefDrawContours
+        from watsor.stream.share import Detection as RefDetection
+        w, h = 640, 480
+        rng = np.random.default_rng(21)
+        with TemporaryDirectory() as tmp:
+            alpha = random_alpha(rng, w, h, 4)
+            path = os.path.join(tmp, 'mask.png')
+            assert cv2.imwrite(path, np.dstack([np.zeros((h, w, 3), np.uint8), alpha]))
+            for config in ({'mask': path, 'width': w, 'height': h}, {'width': w, 'height': h}):
+                img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+                rows = random_rows(rng, w, h, 20, n_zones=4 if 'mask' in config else 0)
+                theirs_hdr = types.SimpleNamespace(
+                    detections=(RefDetection * len(rows)).from_buffer_copy(bytes(rows)))
+                theirs = np.zeros_like(img)
+                if 'mask' in config:
+                    RefBlend(config).apply(img, theirs, img.shape, theirs_hdr, theirs_hdr)
+                    RefDrawContours(config).apply(img, theirs, img.shape, theirs_hdr, theirs_hdr)
+                else:
+                    RefCopy().apply(img, theirs, img.shape, theirs_hdr, theirs_hdr)
+                    RefDraw().apply(img, theirs, img.shape, theirs_hdr, theirs_hdr)
+                ours = np.zeros_like(img)
+                hdr = header_of(rows)
+                FusedEffects(config, engine).apply(img, ours, img.shape, hdr, hdr)
+                assert np.array_equal(theirs, ours), ('mask' in config, int((theirs != ours).sum()))
+    finally:
+        sys.path.remove(ref_root)
+        for k in [k for k in sys.modules if k == 'shapely' or k.startswith('shapely.') or k == 'watsor' or
+                  k.startswith('watsor.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)

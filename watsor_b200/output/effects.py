@@ -11,7 +11,7 @@ thickness 1 is the box outline, cv2.addWeighted is one float fused multiply-add 
 and the zone outlines come from tables made with the installed OpenCV (font.py, `contour_bits`).
 """
 import ctypes
-from ctypes import POINTER, Structure, byref, c_float, c_int32, c_uint8, c_void_p, cast, memmove, sizeof
+from ctypes import Structure, byref, c_float, c_int32, c_uint8, c_void_p, memmove, sizeof
 
 import numpy as np
 
@@ -82,6 +82,7 @@ class EffectsEngine:
         self._fx = c_void_p()
         _check(self.lib.wb_fx_create(device, byref(font), len(labels), table, digits, styles[0].alpha,
                                      byref(self._fx)))
+        self.atlas.lut = None            # 98 MB of host memory: resident on the device now
         self.device = device
         self._next_cam = 0
         self.last_gpu_ms = 0.0
