@@ -189,9 +189,10 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// grid (ceil(W / 128), ceil(H / 32), frames), 256 threads; thread = 4 consecutive pixels in each of 4 rows (the list of
-// detections that touch the tile is built once per block).
-constexpr int FX_TW = 128, FX_TH = 32, FX_ROWS = FX_TH / 8;
+// grid (ceil(W / 128), ceil(H / 8), frames), 256 threads; thread = 4 consecutive pixels of one row.  (FX_TH = 32, four
+// rows per thread and a quarter of the blocks, measured 45 % slower: the pass is bound by the latency of the dependent
+// table loads, and more resident threads hide it better than fewer culling preambles.)
+constexpr int FX_TW = 128, FX_TH = 8, FX_ROWS = FX_TH / 8;
 
 __global__ void __launch_bounds__(256)
     k_fx_render(const FxFrameDesc* __restrict__ frames, const FxFrame* __restrict__ prep, FxFont font,
