@@ -32,13 +32,21 @@ PARITY PINNING STATUS
     watsor/test/model/cpu.pb (tools/make_golden_cvdnn.py, vectors in
     tests/golden/cvdnn_heads.npz labelled "OpenCV-dnn, not TensorFlow",
     tests/test_oracle_cvdnn.py: agreement to 4e-5 on tensors of range 21).
-  - legacy ResizeBilinear, anchor generator, box decode, sigmoid,
-    NonMaxSuppressionV5, top-100 assembly: **parity unpinned**.  The reference
-    holds no golden boxes/scores for the TF graph (watsor/test/test_detect.py:28-77
-    only asserts ">= 100 labelled detections with confidence >= 0.5"), and
-    TensorFlow cannot be run here.  These parts are checked against that same
-    behavioural assertion and otherwise stand on their line-by-line restatement of
-    the GraphDef and of TF's kernel semantics (quoted in oracle/ssd_graph.py).
+  - legacy ResizeBilinear: pinned by OpenCV-dnn executing the reference's own
+    ResizeBilinear node (attributes untouched) with its own kernel, 8 frame sizes,
+    up- and down-scaling, agreement to 2.4e-7 (tests/test_oracle_cvdnn_resize.py).
+  - box decode, per-class greedy NMS, cross-class top-100: pinned by OpenCV-dnn's
+    DetectionOutputLayer (the SSD post-processing of the Caffe / OpenCV model zoos:
+    CENTER_SIZE coding with variances = the graph's scale factors, strict
+    thresholds, greedy order), same detections to 2e-6 on 3-class and 90-class
+    heads with real suppression going on (tests/test_oracle_cvdnn_post.py).
+  - anchors: not restated at all -- constant-folded from the reference's own graph.
+  - still **parity unpinned** (no second executor; TensorFlow cannot run here and
+    the reference's only model test asserts a detection count,
+    watsor/test/test_detect.py:28-77): TF's order for EXACTLY equal scores (lower
+    anchor index first) and the placement of ClipToWindow / zero-area pruning
+    between NMS and the final top-100.  Both follow the GraphDef node order quoted
+    in oracle/ssd_graph.py.
   - oracle/ties.py: float64 classification of rounding ties in the ranking (used by
     the 90-class end-to-end tests); test infrastructure like the rest.
 """

@@ -1,10 +1,12 @@
 """CPU restatement of the frozen TF Object-Detection SSD graph that
 watsor/detection/tensorflow_cpu.py:104-121 runs with `sess.run`.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The conv stack is pinned by OpenCV-dnn running the same
-graph (tests/test_oracle_cvdnn.py); for resize / decode / NMS it is "parity unpinned": the
-reference holds no golden vectors at the TF boundary and TensorFlow cannot run
-here; this file follows the GraphDef node by node (node names quoted below) and is
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Every arithmetic stage is pinned by OpenCV-dnn as an independent
+executor: the conv stack on the reference's own graph (tests/test_oracle_cvdnn.py), the legacy resize on the
+reference's own node (tests/test_oracle_cvdnn_resize.py), decode / NMS / top-100 against DetectionOutputLayer
+(tests/test_oracle_cvdnn_post.py).  "Parity unpinned" remains for the order of exactly equal scores and the position
+of ClipToWindow / pruning in the top-100 assembly: the reference holds no golden vectors at the TF boundary and
+TensorFlow cannot run here; this file follows the GraphDef node by node (node names quoted below) and is
 sanity-pinned on the reference's behavioural test (test_detect.py:28-77).
 
 The graph (watsor/test/model/cpu.pb) is, per image:
