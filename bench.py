@@ -20,9 +20,14 @@ confidence/area/mask-zone predicates -> Detection[100] per frame.
          H2D of every frame and D2H of every Detection block inside the timed region
   config.real_weights   the same two numbers on the only model with real weights (the reference's vendored
          3-class SSD-MobileNet-v1, watsor/test/model/cpu.pb), porch mask on camera 0
+  e2e_worker   the same metric through the drop-in worker process (watsor_b200.detection.detector.ObjectDetector
+         under `spawn`, frames in multiprocessing shared memory, payloads through a Queue)
+  effects      auxiliary (not the headline): the output stage's effect chain -- BlendEffect +
+         DrawEffectWithContours -- for the same cameras as one wb_fx_render per tick
 Multi-GPU: one process per GPU (torchrun), cameras sharded, no data-path collective (weak scaling); the
 N>1 line adds a `scatter` record: the same steps with the NCCL frame scatter from rank 0 that BASELINE.json's
-north star names.
+north star names, through the library's own collective (wb_comm_init / wb_scatter_frames; --scatter-impl torch
+runs torch.distributed.scatter instead).
 """
 import argparse
 import json

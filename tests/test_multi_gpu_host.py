@@ -20,7 +20,8 @@ def free_port():
 
 def worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
-    from watsor_b200.parallel import camera_shard, max_over_ranks, scatter_frames, sum_over_ranks
+    from watsor_b200.parallel import (camera_shard, engine_scatter_frames, init_engine_comm, max_over_ranks,
+                                      scatter_frames, sum_over_ranks)
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -33,6 +34,35 @@ def worker(rank, world, port, out):
     recv = torch.empty((C, H, W, 3), dtype=torch.uint8)
     scatter_frames(recv, per_rank, src=0)
     ok = all(int(recv[c].min()) == cams[c] == int(recv[c].max()) for c in range(C))
+    # rendezvous of the library's own communicator (wb_comm_init): the id is made by the C-ABI on the root and must
+    # reach every rank unchanged; the engine here records the calls (the collective itself needs GPUs:
+    # tests/test_gpu_scatter.py)
+    class RecordingEngine:
+        def __init__(self):
+            from watsor_b200 import _lib
+            self.lib, self.calls = _lib.load(), []
+
+        def comm_unique_id(self):
+            import ctypes
+            buf = (ctypes.c_uint8 * 128)()
+            assert self.lib.wb_comm_unique_id(buf) == 0
+            return bytes(buf)
+
+        def comm_init(self, rank, world, unique_id):
+            self.calls.append(('init', rank, world, bytes(unique_id)))
+
+        def scatter_frames(self, root, send, recv, nbytes, cuda_stream=0):
+            self.calls.append(('scatter', root, None if send is None else len(send), nbytes))
+
+    eng = RecordingEngine()
+    init_engine_comm(eng, rank, world)
+    engine_scatter_frames(eng, recv, per_rank, root=0)
+    ident = eng.calls[0][3]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ident)
+    ok = ok and eng.calls[0][:3] == ('init', rank, world) and len(ident) == 128 and any(ident) and \
+        all(g == ident for g in gathered) and \
+        eng.calls[1] == ('scatter', 0, world if rank == 0 else None, C * H * W * 3)
     slowest = max_over_ranks(1.0 + rank)
     frames = sum_over_ranks(C * 10)
     dist.barrier()
