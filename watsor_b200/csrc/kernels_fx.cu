@@ -189,10 +189,12 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// grid (ceil(W / 128), ceil(H / 8), frames), 256 threads; thread = 4 consecutive pixels of one row.  (FX_TH = 32, four
-// rows per thread and a quarter of the blocks, measured 45 % slower: the pass is bound by the latency of the dependent
-// table loads, and more resident threads hide it better than fewer culling preambles.)
-constexpr int FX_TW = 128, FX_TH = 8, FX_ROWS = FX_TH / 8;
+// grid (ceil(W / 128), ceil(H / 8), frames), 256 threads; thread = 4 consecutive pixels of one row.  (32-row tiles with
+// four rows per thread and a quarter of the blocks measured 45 % slower: the pass is bound by the latency of dependent
+// loads, and more resident threads hide it better than fewer culling preambles.)  For the same reason a thread issues
+// the loads of its pixels, alpha values and outline bits first and only then takes part in building the tile's list of
+// detections, so that the two chains of global round trips overlap.
+constexpr int FX_TW = 128, FX_TH = 8;
 
 __global__ void __launch_bounds__(256)
     k_fx_render(const FxFrameDesc* __restrict__ frames, const FxFrame* __restrict__ prep, FxFont font,
@@ -207,57 +209,102 @@ __global__ void __launch_bounds__(256)
   if (tx0 >= W || ty0 >= H) return;
   const int tx1 = min(tx0 + FX_TW, W), ty1 = min(ty0 + FX_TH, H);
   const int t = threadIdx.x;
-  // detections that can touch this tile, in row order
-  int n_here = 0;
-  if (flags & WB_FX_DRAW) {
-    const int na = fr.n_active;
-    bool hit = false;
-    int idx = 0;
-    if (t < na) {
-      idx = fr.order[t];
-      const FxDet& d = fr.det[idx];
-      const bool rect = d.x0 < tx1 && d.x1 >= tx0 && d.y0 < ty1 && d.y1 >= ty0;
-      const bool box = d.bx0 < tx1 && max(d.bx1, d.text_x1) > tx0 && d.by0 < ty1 && d.by1 > ty0 && d.by1 > d.by0;
-      hit = rect || box;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (t < 128 && (t & 31) == 0) s_hit[t >> 5] = m;
-    __syncthreads();
-    if (hit) {
-      int pos = __popc(m & ((1u << (t & 31)) - 1u));
-      for (int w = 0; w < (t >> 5); ++w) pos += __popc(s_hit[w]);
-      s_det[pos] = fr.det[idx];
-    }
-    if (t == 0) s_n = __popc(s_hit[0]) + __popc(s_hit[1]) + __popc(s_hit[2]) + __popc(s_hit[3]);
-    __syncthreads();
-    n_here = s_n;
-  }
+  const int y = ty0 + t / (FX_TW / 4);
   const int xb = tx0 + (t % (FX_TW / 4)) * 4;
-  if (xb >= W) return;
-  for (int j = 0; j < FX_ROWS; ++j) {
-  const int y = ty0 + t / (FX_TW / 4) + 8 * j;
-  if (y >= H) break;
-  const size_t row = (size_t)y * W;
-  const int npx = min(4, W - xb);
-  uint8_t v[4][3];
-  const uint8_t* src = fd.in + (row + xb) * 3;
-  uint8_t* dst = fd.out + (row + xb) * 3;
+  const bool live = y < H && xb < W;  // threads outside the frame still take part in the barriers below
+  const size_t row = (size_t)(live ? y : 0) * W;
+  const int npx = live ? min(4, W - xb) : 0;
+  const size_t px0 = row + (live ? xb : 0);
+  const uint8_t* src = fd.in + px0 * 3;
+  uint8_t* dst = fd.out + px0 * 3;
+  const bool blend = (flags & WB_FX_BLEND) && fd.cam.alpha != nullptr;
+  const bool outline = (flags & WB_FX_CONTOURS) && fd.cam.contours != nullptr;
   const bool vec = npx == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
+  // ---- loads first
+  uint32_t ws[3] = {0u, 0u, 0u};
+  uint8_t v[4][3];
+  uint8_t al[4] = {255, 255, 255, 255};
+  uint32_t cb[4] = {0u, 0u, 0u, 0u};
   if (vec) {
     const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-    const uint32_t w0 = __ldg(s32), w1 = __ldg(s32 + 1), w2 = __ldg(s32 + 2);
-    const uint32_t ws[3] = {w0, w1, w2};
+    ws[0] = __ldg(s32);
+    ws[1] = __ldg(s32 + 1);
+    ws[2] = __ldg(s32 + 2);
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (p < npx) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[p][c] = __ldg(src + p * 3 + c);
+      }
+  }
+  if (blend) {
+    const uint8_t* ap = fd.cam.alpha + px0;
+    if (npx == 4 && (reinterpret_cast<uintptr_t>(ap) & 3) == 0) {
+      const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t*>(ap));
+#pragma unroll
+      for (int p = 0; p < 4; ++p) al[p] = (uint8_t)(a4 >> (8 * p));
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < npx) al[p] = __ldg(ap + p);
+    }
+  }
+  if (outline) {
+    const uint32_t* cp = fd.cam.contours + px0;
+    if (npx == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+      const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cp));
+      cb[0] = c4.x;
+      cb[1] = c4.y;
+      cb[2] = c4.z;
+      cb[3] = c4.w;
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < npx) cb[p] = __ldg(cp + p);
+    }
+  }
+  // ---- detections that can touch this tile, in row order
+  int n_here = 0;
+  uint32_t zone_sel = 0u;
+  if (flags & WB_FX_DRAW) {
+    const int na = fr.n_active;
+    zone_sel = fr.zone_sel;
+    if (na > 0) {  // uniform
+      bool hit = false;
+      int idx = 0;
+      if (t < na) {
+        idx = fr.order[t];
+        const FxDet& d = fr.det[idx];
+        const bool rect = d.x0 < tx1 && d.x1 >= tx0 && d.y0 < ty1 && d.y1 >= ty0;
+        const bool box = d.bx0 < tx1 && max(d.bx1, d.text_x1) > tx0 && d.by0 < ty1 && d.by1 > ty0 && d.by1 > d.by0;
+        hit = rect || box;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (t < 128 && (t & 31) == 0) s_hit[t >> 5] = m;
+      __syncthreads();
+      if (hit) {
+        int pos = __popc(m & ((1u << (t & 31)) - 1u));
+        for (int w = 0; w < (t >> 5); ++w) pos += __popc(s_hit[w]);
+        s_det[pos] = fr.det[idx];
+      }
+      if (t == 0) s_n = __popc(s_hit[0]) + __popc(s_hit[1]) + __popc(s_hit[2]) + __popc(s_hit[3]);
+      __syncthreads();
+      n_here = s_n;
+    }
+  }
+  if (!live) return;
+  if (vec) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) v[i / 3][i % 3] = (uint8_t)(ws[i >> 2] >> (8 * (i & 3)));
-  } else {
-    for (int p = 0; p < npx; ++p)
-      for (int c = 0; c < 3; ++c) v[p][c] = __ldg(src + p * 3 + c);
   }
   // CopyImageEffect / BlendEffect
-  if ((flags & WB_FX_BLEND) && fd.cam.alpha != nullptr) {
-    for (int p = 0; p < npx; ++p) {
-      const float af = __fdiv_rn((float)__ldg(fd.cam.alpha + row + xb + p), 255.f);  // blend.py:15
-      const float wi = __fmul_rn(255.f, __fsub_rn(1.f, af));                          // blend.py:21-22
+  if (blend) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p >= npx) continue;
+      const float af = __fdiv_rn((float)al[p], 255.f);         // blend.py:15
+      const float wi = __fmul_rn(255.f, __fsub_rn(1.f, af));   // blend.py:21-22
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         v[p][c] = (uint8_t)__float2int_rz(__fadd_rn(__fmul_rn((float)v[p][c], af), wi));  // blend.py:28-32
@@ -273,7 +320,9 @@ __global__ void __launch_bounds__(256)
     const int gy = y - (d.oy + font.y0);
     const bool text_y = d.n_glyphs > 0 && gy >= 0 && gy < font.rows;
     if (!in_y && !box_y && !text_y) continue;
-    for (int p = 0; p < npx; ++p) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p >= npx) continue;
       const int x = xb + p;
       if ((on_h && x >= d.x0 && x <= d.x1) || (in_y && (x == d.x0 || x == d.x1))) {  // cv2.rectangle, thickness 1
         v[p][0] = col[0];
@@ -305,27 +354,31 @@ __global__ void __launch_bounds__(256)
     }
   }
   // DrawEffectWithContours: outline every zone some drawn detection lies in (draw.py:100-103), colour (255, 255, 0)
-  if ((flags & WB_FX_CONTOURS) && fd.cam.contours != nullptr && fr.zone_sel != 0u) {
-    for (int p = 0; p < npx; ++p)
-      if (__ldg(fd.cam.contours + row + xb + p) & fr.zone_sel) {
+  if (outline && zone_sel != 0u) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (p < npx && (cb[p] & zone_sel)) {
         v[p][0] = 255;
         v[p][1] = 255;
         v[p][2] = 0;
       }
   }
   if (vec) {
-    uint32_t ws[3] = {0u, 0u, 0u};
+    uint32_t wo[3] = {0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 12; ++i) ws[i >> 2] |= (uint32_t)v[i / 3][i % 3] << (8 * (i & 3));
+    for (int i = 0; i < 12; ++i) wo[i >> 2] |= (uint32_t)v[i / 3][i % 3] << (8 * (i & 3));
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-    d32[0] = ws[0];
-    d32[1] = ws[1];
-    d32[2] = ws[2];
+    d32[0] = wo[0];
+    d32[1] = wo[1];
+    d32[2] = wo[2];
   } else {
-    for (int p = 0; p < npx; ++p)
-      for (int c = 0; c < 3; ++c) dst[p * 3 + c] = v[p][c];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (p < npx) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[p * 3 + c] = v[p][c];
+      }
   }
-  }  // rows of this thread
 }
 
 }  // namespace
