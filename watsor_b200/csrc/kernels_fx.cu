@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128)
 constexpr int FX_TW = 128, FX_TH = 8;
 
 // (forcing 32 registers for 8 blocks per SM instead of 5 spills and measured 8 % slower)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
     k_fx_render(const FxFrameDesc* __restrict__ frames, const FxFrame* __restrict__ prep, FxFont font,
                 const FxLabel* __restrict__ labels, const uint8_t* __restrict__ aw_lut, uint32_t flags) {
   __shared__ FxDet s_det[WB_MAX_DETECTIONS];
