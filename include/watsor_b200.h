@@ -120,9 +120,11 @@ int wb_unregister_host(wb_ctx* ctx, void* ptr);
 int wb_detect(wb_ctx* ctx, int n, const uint8_t* const* frames, const int32_t* cam_ids,
               uint32_t flags, wb_detection* const* out, uint32_t* const* verdicts, float* gpu_ms);
 
-/* two-slot asynchronous form of wb_detect: submit() enqueues H2D + kernels + D2H on the slot's
- * stream and returns; collect() waits and scatters results.  Lets host ingest of batch k+1 overlap
- * the kernels of batch k (the reference overlaps them with processes, detector.py:40-50). */
+/* asynchronous form of wb_detect over slots 0..5 (stream + arena + staging each): submit() enqueues H2D +
+ * kernels + D2H on the slot's stream and returns; collect() waits and scatters results.  Lets host ingest of
+ * batch k+1 overlap the kernels of batch k (the reference overlaps them with processes, detector.py:40-50),
+ * and several batches in flight are what keeps a B200's SMs busy.  Thread-safe: a mutex in
+ * the context serialises the calls that touch shared state. */
 int wb_submit(wb_ctx* ctx, int slot, int n, const uint8_t* const* frames, const int32_t* cam_ids,
               uint32_t flags);
 int wb_collect(wb_ctx* ctx, int slot, wb_detection* const* out, uint32_t* const* verdicts,
