@@ -438,6 +438,12 @@ class Arm:
             self.run_device_steps(2 * self.NS, primed)
             primed += 2 * self.NS
         self.prime_steps = primed
+        if world > 1:
+            # ranks finish priming at different times (process start-up differs by 100s of ms); without this the early
+            # ranks would sit idle in the timed region's opening barrier, clock down, and the maximum over ranks of a
+            # short K-step region would measure their ramp-up.  Aligned here, the W warm-up steps below run on every
+            # rank right before that barrier, which then costs microseconds.
+            self.barrier()
         self.run_device_steps(warm, 0)
         launches = self.det.engine.last_launch_count()
         dev_ms, t_wall = self.time_device(args.steps, args.warmup)
